@@ -1,0 +1,153 @@
+/*
+ * thylacine_b200.h -- C ABI of the B200-native posterior-evaluation hot path.
+ *
+ * The reference (gvonness/thylacine, Scala) has no FFI boundary; this header CREATES the seam at the
+ * reference's L5/L6 trait surface.  Each entry point cites the reference interface
+ * it replaces as path:line relative to /root/reference/src/main/scala/thylacine/.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no C++ or torch types; every call returns a thy_status (0 = ok);
+ *   - all numbers are IEEE fp64; parameter batches are row-major "chain-major": X[b*d + j];
+ *   - a handle is used by one caller at a time; distinct handles may be used concurrently;
+ *   - the library owns all device memory; callers own host buffers; inputs are copied at add / finalize;
+ *   - there is NO CPU fallback: every evaluation entry point returns THY_ERR_NO_DEVICE without a GPU;
+ *   - *_dev variants take device pointers on the current CUDA device and are asynchronous on the
+ *     stream set by thy_model_set_stream (default: the legacy default stream).
+ */
+#ifndef THYLACINE_B200_H
+#define THYLACINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum thy_status {
+  THY_OK = 0,
+  THY_ERR_INVALID_ARGUMENT = 1, /* what the reference asserts: dimension mismatch, CI <= 0, hi <= lo, duplicates */
+  THY_ERR_UNKNOWN_LABEL = 2,    /* IndexedCollection.scala:25-31 RuntimeException */
+  THY_ERR_CUDA = 3,
+  THY_ERR_NCCL = 4,
+  THY_ERR_STATE = 5,            /* call order (e.g. evaluate before finalize, add after finalize) */
+  THY_ERR_UNSUPPORTED = 6,
+  THY_ERR_NO_DEVICE = 7
+} thy_status;
+
+typedef struct thy_model_s* thy_model_t;
+typedef struct thy_hmc_s* thy_hmc_t;
+typedef struct thy_lfm_s* thy_lfm_t;
+typedef struct thy_slq_s* thy_slq_t;
+
+/* ---- library ------------------------------------------------------------------------------------- */
+const char* thy_version(void);
+/* Message of the last failing call on this thread (never NULL). */
+const char* thy_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches claim). */
+uint64_t thy_kernel_launch_count(void);
+
+/* ---- model construction --------------------------------------------------------------------------
+ * Replaces the Scala case-class constructors; the model is immutable after thy_model_finalize (mirrors
+ * the reference's immutable case classes).                                                            */
+thy_status thy_model_create(thy_model_t* out);
+thy_status thy_model_destroy(thy_model_t m);
+
+/* GaussianPrior.fromConfidenceIntervals(label, values, confidenceIntervals)
+ *   components/prior/GaussianPrior.scala:62-75; variance = (ci/2)^2, core/RecordedData.scala:59-66. */
+thy_status thy_model_add_gaussian_prior_ci(thy_model_t m, const char* label, int dim,
+                                           const double* values, const double* confidence_intervals);
+/* GaussianPrior.fromCovarianceMatrix(label, values, covarianceMatrix)  GaussianPrior.scala:78-93
+ *   covariance: dim x dim row-major, symmetric positive definite.                                     */
+thy_status thy_model_add_gaussian_prior_cov(thy_model_t m, const char* label, int dim,
+                                            const double* values, const double* covariance);
+/* UniformPrior.fromBounds(label, maxBounds, minBounds)  components/prior/UniformPrior.scala:68-77
+ *   (argument order max-then-min as in the reference); box is half-open [min, max),
+ *   distributions/UniformDistribution.scala:61-66.                                                    */
+thy_status thy_model_add_uniform_prior(thy_model_t m, const char* label, int dim,
+                                       const double* max_bounds, const double* min_bounds);
+/* CauchyPrior(label, values, confidenceIntervals)  components/prior/CauchyPrior.scala:50-63 */
+thy_status thy_model_add_cauchy_prior(thy_model_t m, const char* label, int dim,
+                                      const double* values, const double* confidence_intervals);
+
+/* Observation distribution of a likelihood (distributions/{Gaussian,Cauchy,Uniform}Distribution.scala). */
+typedef enum thy_distribution { THY_DIST_GAUSSIAN = 0, THY_DIST_CAUCHY = 1, THY_DIST_UNIFORM = 2 } thy_distribution;
+
+/* Forward-model families.  A JVM closure (NonLinearForwardModel.of(evaluation = ...),
+ * forwardmodel/NonLinearForwardModel.scala:44-85) cannot run on a GPU; the device-side registry is
+ * f(theta) = link(A . theta + offset) applied element-wise.  THY_LINK_IDENTITY with THY_JAC_CONSTANT is the
+ * reference's LinearForwardModel (forwardmodel/LinearForwardModel.scala:76-114).                        */
+typedef enum thy_link {
+  THY_LINK_IDENTITY = 0, THY_LINK_TANH = 1, THY_LINK_EXP = 2, THY_LINK_SQUARE = 3,
+  THY_LINK_SOFTPLUS = 4, THY_LINK_SIGMOID = 5
+} thy_link;
+
+typedef enum thy_jacobian {
+  THY_JAC_CONSTANT = 0,           /* LinearForwardModel.jacobianAt: the coefficient blocks (:65-71)            */
+  THY_JAC_ANALYTIC = 1,           /* NonLinearForwardModel.of(evaluation, jacobian, ...) (:64-85): link'(z) A   */
+  THY_JAC_FINITE_DIFFERENCE = 2   /* core/computation/FiniteDifferenceJacobian.scala:30-55, forward difference, */
+                                  /* all d_total+1 perturbed models evaluated in one launch                     */
+} thy_jacobian;
+
+typedef struct thy_likelihood_desc {
+  int distribution;               /* thy_distribution                                                          */
+  int link;                       /* thy_link                                                                  */
+  int jacobian;                   /* thy_jacobian (THY_JAC_CONSTANT requires THY_LINK_IDENTITY)                */
+  int n;                          /* range dimension (number of observations)                                  */
+  int nblocks;                    /* labelled coefficient blocks (IndexedMatrixCollection)                     */
+  const char* const* labels;      /* [nblocks] prior labels this forward model reads                           */
+  const int* dims;                /* [nblocks] block widths; must equal the prior dimensions                   */
+  const double* const* blocks;    /* [nblocks] each n x dims[i], row-major (row = observation)                 */
+  const double* offset;           /* [n] or NULL: LinearForwardModel vectorOffset (:103-104)                   */
+  const double* measurements;     /* [n]  Gaussian/Cauchy: observed values;  Uniform: upperBounds              */
+  const double* uncertainties;    /* [n]  Gaussian/Cauchy: confidence intervals (sigma = ci/2); Uniform: lowerBounds */
+  double differential;            /* finite-difference step (NonLinearForwardModel.of(differential = ...))     */
+} thy_likelihood_desc;
+
+/* GaussianLinearLikelihood.of / GaussianLikelihood.apply / CauchyLikelihood.apply,.of / UniformLikelihood.apply
+ *   components/likelihood/{GaussianLinearLikelihood.scala:62-83, GaussianLikelihood.scala:55-67,
+ *   CauchyLikelihood.scala:59-92, UniformLikelihood.scala:63-73}.  Must follow the priors it refers to. */
+thy_status thy_model_add_likelihood(thy_model_t m, const thy_likelihood_desc* desc);
+
+/* Options (set before finalize). */
+typedef enum thy_option {
+  /* 1 (default) = reproduce CauchyDistribution.scala:70-79 literally (gradient has the wrong sign);
+   * 0 = mathematically correct sign.  Samplers built on a model always use the correct sign.             */
+  THY_OPT_CAUCHY_REFERENCE_SIGN = 0,
+  /* Finite-difference evaluation: 0 (default) = every perturbed point theta + h e_j goes through the full
+   * forward model (the reference's arithmetic); 1 = incremental z + h A[:,j] (same limit, fewer flops).   */
+  THY_OPT_FD_INCREMENTAL = 1,
+  /* Kernel selection for linear-Gaussian terms: 0 = auto, 1 = force generic tiled kernels,
+   * 2 = force fused DMMA kernel (error if the shape is unsupported), 3 = force streaming (small-batch) kernel. */
+  THY_OPT_KERNEL_PATH = 2
+} thy_option;
+thy_status thy_model_set_option(thy_model_t m, int option, int value);
+
+/* Sorts labels ascending (posterior/Posterior.scala:40-48, core/GenericIdentifier.scala:29-30), builds the flat
+ * layout, validates every likelihood label against the priors, uploads constants to the current device.   */
+thy_status thy_model_finalize(thy_model_t m);
+/* domainDimension (Posterior.scala:37-38) */
+thy_status thy_model_dimension(thy_model_t m, int* out_dim);
+/* offset and width of a label inside the flat vector (ModelParameterContext.scala:42-80) */
+thy_status thy_model_label_layout(thy_model_t m, const char* label, int* out_offset, int* out_dim);
+/* Stream used by the *_dev entry points and by samplers built on this model (a cudaStream_t). */
+thy_status thy_model_set_stream(thy_model_t m, void* cuda_stream);
+thy_status thy_model_synchronize(thy_model_t m);
+
+/* ---- evaluation ----------------------------------------------------------------------------------
+ * ModelParameterPdf.logPdfAt / logPdfGradientAt  (core/values/modelparameters/ModelParameterPdf.scala:33-46,84-95),
+ * Posterior.logPdfAt / logPdfGradientAt (posterior/Posterior.scala:50-73), batched over B points.       */
+thy_status thy_logpdf_batch(thy_model_t m, int64_t B, const double* X, double* out_logp);
+thy_status thy_logpdf_grad_batch(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad);
+/* Device-pointer variants (zero-copy; out_grad may be NULL for value only). */
+thy_status thy_logpdf_grad_batch_dev(thy_model_t m, int64_t B, const double* X_dev, double* logp_dev, double* grad_dev);
+/* Posterior.samplePriors (Posterior.scala:64-65): B independent prior draws with the counter-based RNG. */
+thy_status thy_sample_priors(thy_model_t m, int64_t B, uint64_t rng_seed, double* out_X);
+thy_status thy_sample_priors_dev(thy_model_t m, int64_t B, uint64_t rng_seed, double* X_dev);
+/* Name of the kernel path the last evaluation on this model used ("fused_dmma", "stream", "generic", ...). */
+const char* thy_model_last_kernel_path(thy_model_t m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THYLACINE_B200_H */

@@ -1,0 +1,159 @@
+"""The oracle against every golden vector the reference's own tests hold for this path.
+
+Reference specs (paths relative to /root/reference/src/test/scala/thylacine/):
+  model/components/prior/GaussianPriorSpec.scala:25-58
+  model/components/likelihood/GaussianLinearLikelihoodSpec.scala:32-48
+  model/components/likelihood/GaussianLikelihoodSpec.scala:33-49
+  model/components/posterior/GaussianAnalyticPosteriorSpec.scala:34-50
+  model/components/ComponentFixture.scala:29-211 (fixture values)
+"""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ref_oracle as o
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "reference_specs.json").read_text())
+
+
+def test_confidence_interval_to_variance():
+    # GaussianPriorSpec.scala:25-35,37-47: covariance == Math.pow(ci / 2, 2)
+    assert o.ci_to_variance([3.0])[0] == 2.25
+    p = o.gaussian_prior_from_ci("p", [1, 2], [3, 5])
+    assert np.array_equal(np.diag(p.distribution.covariance), [math.pow(1.5, 2), math.pow(2.5, 2)])
+
+
+def test_gaussian_prior_gradient_exact():
+    g = GOLDEN["gaussian_prior_gradient"]
+    p = o.gaussian_prior_from_ci("p", g["mean"], g["ci"])
+    got = p.log_pdf_gradient({"p": np.array(g["x"], dtype=float)})["p"]
+    assert np.array_equal(got, np.array([-0.25, 4.0 / 9.0, -1.0]))          # exact equality, as the spec demands
+
+
+def test_gaussian_linear_likelihood_gradient_exact():
+    f = GOLDEN["foo_likelihood"]
+    lk = o.gaussian_linear_likelihood(f["A"], f["y"], f["ci"], "foo")
+    assert np.array_equal(lk.log_pdf_gradient({"foo": np.array([1.0, 2.0])})["foo"], [0.0, 0.0])
+    assert np.array_equal(lk.log_pdf_gradient({"foo": np.array([3.0, 2.0])})["foo"], [-4e5, -8.8e5])
+
+
+def test_gaussian_likelihood_fd_gradient():
+    f = GOLDEN["foo_likelihood"]
+    A = np.array(f["A"], dtype=float)
+    fm = o.NonLinearForwardModel(lambda p: A @ p["foo"], 1e-4, {"foo": 2}, 2)
+    lk = o.gaussian_likelihood(fm, f["y"], f["ci"])
+    assert np.array_equal(lk.log_pdf_gradient({"foo": np.array([1.0, 2.0])})["foo"], [0.0, 0.0])
+    got = lk.log_pdf_gradient({"foo": np.array([3.0, 2.0])})["foo"]
+    assert np.max(np.abs(got - np.array([-4e5, -8.8e5]))) < 1e-4            # GaussianLikelihoodSpec.scala:46-48
+
+
+def test_derived_logpdf_values():
+    # SURVEY 8c derived known answers (formula a7 with the fixture inputs)
+    f = GOLDEN["foo_likelihood"]
+    lk = o.gaussian_linear_likelihood(f["A"], f["y"], f["ci"], "foo")
+    assert lk.log_pdf({"foo": np.array([1.0, 2.0])}) == pytest.approx(8.758757666686726, rel=1e-14)
+    assert lk.log_pdf({"foo": np.array([3.0, 2.0])}) == pytest.approx(-399991.2412423333, rel=1e-14)
+    p = o.gaussian_prior_from_ci("foo", [1, 2], [3, 5])
+    assert p.log_pdf({"foo": np.array([1.0, 2.0])}) == pytest.approx(-3.159632906391665, rel=1e-14)
+    assert p.log_pdf({"foo": np.array([3.0, 2.0])}) == pytest.approx(-4.0485217952805534, rel=1e-14)
+    assert np.allclose(p.log_pdf_gradient({"foo": np.array([3.0, 2.0])})["foo"], [-8.0 / 9.0, 0.0], rtol=1e-15)
+
+
+def test_cauchy_reference_formula_and_sign_quirk():
+    f = GOLDEN["foo_likelihood"]
+    fm = o.LinearForwardModel({"foo": f["A"]})
+    lk = o.cauchy_likelihood(fm, f["y"], f["ci"], reference_faithful=True)
+    x = {"foo": np.array([3.0, 2.0])}
+    assert lk.log_pdf(x) == pytest.approx(-11.6297947182872, rel=1e-12)
+    g_ref = lk.log_pdf_gradient(x)["foo"]
+    assert np.allclose(g_ref, [1.49999813, 3.29999588], rtol=1e-7)          # uphill: SURVEY Q3
+    g_ok = o.cauchy_likelihood(fm, f["y"], f["ci"], reference_faithful=False).log_pdf_gradient(x)["foo"]
+    assert np.allclose(g_ok, -g_ref)
+    # the correct sign agrees with a central difference of the reference's own logPdf
+    h = 1e-6
+    num = [(lk.log_pdf({"foo": x["foo"] + h * e}) - lk.log_pdf({"foo": x["foo"] - h * e})) / (2 * h) for e in np.eye(2)]
+    assert np.allclose(g_ok, num, rtol=1e-5)
+    # lgamma / log-det normaliser == Gamma.gamma / det normaliser where the latter is finite (Q4)
+    a = o.CauchyDistribution.from_ci(f["y"], f["ci"], True).log_multiplier
+    b = o.CauchyDistribution.from_ci(f["y"], f["ci"], False).log_multiplier
+    assert a == pytest.approx(b, rel=1e-13)
+
+
+def test_uniform_half_open():
+    u = o.UniformDistribution([5, 5], [-5, -5])
+    assert u.log_pdf([0, 0]) == pytest.approx(-2 * math.log(10))
+    assert u.log_pdf([-5, 0]) == pytest.approx(-2 * math.log(10))           # lower bound inclusive
+    assert u.log_pdf([5, 0]) == -math.inf                                    # upper bound exclusive
+    assert np.array_equal(u.log_pdf_gradient([0, 0]), [0, 0])
+
+
+def test_analytic_posterior_spec():
+    # GaussianAnalyticPosteriorSpec.scala:34-50: mean ~ foo (1,2), bar 5 within 0.1; covariance ~ 0 within 0.01
+    foo, bar = GOLDEN["foo_likelihood"], GOLDEN["bar_likelihood"]
+    # flat order: "bar" < "foo"
+    A = np.zeros((4, 3))
+    A[0:2, 1:3] = foo["A"]
+    A[2:4, 0:1] = bar["A"]
+    y = np.array(foo["y"] + bar["y"], dtype=float)
+    var = o.ci_to_variance(foo["ci"] + bar["ci"])
+    pm = np.array([5.0, 1.0, 2.0])
+    pv = o.ci_to_variance([0.1, 3.0, 5.0])
+    mean, cov = o.analytic_gaussian_posterior(pm, pv, A, y, var)
+    assert np.max(np.abs(mean - np.array([5.0, 1.0, 2.0]))) < 0.1
+    assert np.max(np.abs(cov)) < 0.01
+
+
+def test_posterior_flatten_order_is_label_sorted():
+    pri = [o.gaussian_prior_from_ci("foo", [1, 2], [3, 5]), o.gaussian_prior_from_ci("bar", [5], [0.1])]
+    post = o.Posterior(pri, [])
+    assert post.ordered == [("bar", 1), ("foo", 2)]                         # Posterior.scala:40-48
+    assert np.array_equal(post.flatten({"foo": [1, 2], "bar": [5]}), [5, 1, 2])
+
+
+def test_structured_batch_matches_literal_dense():
+    rng = np.random.default_rng(7)
+    n, d, B = 40, 6, 5
+    A = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    ci = rng.uniform(0.1, 1.0, n)
+    pm, pci = rng.standard_normal(d), rng.uniform(1, 3, d)
+    post = o.Posterior([o.gaussian_prior_from_ci("t", pm, pci)], [o.gaussian_linear_likelihood(A, y, ci, "t")])
+    X = rng.standard_normal((B, d))
+    lp, g = o.linear_gaussian_batch(A, y, o.ci_to_variance(ci), X, prior_mean=pm, prior_var=o.ci_to_variance(pci))
+    for b in range(B):
+        assert post.log_pdf(X[b]) == pytest.approx(lp[b], rel=1e-12)
+        assert np.allclose(post.log_pdf_gradient(X[b]), g[b], rtol=1e-11, atol=1e-11 * np.max(np.abs(g[b])))
+        mlp, mg = o.mp_linear_gaussian(A, y, o.ci_to_variance(ci), X[b], pm, o.ci_to_variance(pci))
+        assert mlp == pytest.approx(lp[b], rel=1e-12)
+        assert np.allclose(mg, g[b], rtol=1e-11, atol=1e-12 * np.max(np.abs(g[b])))
+
+
+def test_cdf_staircase():
+    st = o.vector_cdf_staircase([1.0, 3.0, 0.0, 4.0])                        # MathOps.scala:76-91
+    assert st == [(0.0, 0.125), (0.125, 0.5), (0.5, 0.5), (0.5, 1.0)]
+    assert o.staircase_index(st, 0.5) == 3 and o.staircase_index(st, 0.0) == 0 and o.staircase_index(st, 0.49) == 1
+
+
+def test_trapezoid_weights():
+    q = o.QuadratureAbscissa(4, np.random.default_rng(0))
+    for _ in range(5):
+        q.extend_by_one()
+    xs = q.abscissa
+    assert xs[0] == 1.0 and all(a > b for a, b in zip(xs, xs[1:]))          # QuadratureAbscissa.scala:64-73
+    w = q.trapezoid_weights()
+    assert w[0] == 0.5 * (xs[0] - xs[1]) and w[-1] == 0.5 * (xs[-2] - xs[-1]) and w[2] == 0.5 * (xs[1] - xs[3])
+
+
+def test_analytic_evidence_against_quadrature():
+    # 1-d check of ln Z = ln N(y; A mu_p, Sd + A Sp A^T) by brute-force integration
+    A = np.array([[2.0], [-1.0]])
+    y = np.array([1.0, 0.5])
+    var = np.array([0.3, 0.7])
+    pm, pv = np.array([0.2]), np.array([1.5])
+    xs = np.linspace(-12, 12, 200001)
+    lp, _ = o.linear_gaussian_batch(A, y, var, xs[:, None], prior_mean=pm, prior_var=pv, want_grad=False)
+    z = np.trapezoid(np.exp(lp), xs)
+    assert math.log(z) == pytest.approx(o.analytic_gaussian_log_evidence(pm, pv, A, y, var), rel=1e-9)

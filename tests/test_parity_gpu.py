@@ -1,0 +1,299 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors.
+
+Tolerance (north_star): log-posterior and gradient within 1e-10 relative in fp64 -- gradient relative to
+||grad||_inf of the oracle, log-pdf relative to |logpdf| (absolute 1e-10 when |logpdf| < 1).
+"""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import thylacine_b200 as t
+from thylacine_b200 import capi
+from oracle import ref_oracle as o
+from helpers import linear_gaussian_problem, typical_set_points, rel_err_logp, rel_err_grad
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "reference_specs.json").read_text())
+PATHS = [capi.KERNEL_GENERIC, capi.KERNEL_FUSED_DMMA]
+
+
+# ---- the reference's own specs, through the drop-in surface --------------------------------------------
+def test_GaussianPriorSpec_gradient_exact():
+    g = GOLDEN["gaussian_prior_gradient"]
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("p", g["mean"], g["ci"])])
+    got = post.logPdfGradientAt({"p": g["x"]})["p"]
+    assert np.array_equal(got, np.array([-0.25, 4.0 / 9.0, -1.0]))           # GaussianPriorSpec.scala:57
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_GaussianLinearLikelihoodSpec_gradient_exact(path):
+    f = GOLDEN["foo_likelihood"]
+    # a flat improper-ish prior is not available in the reference either: use the uniform fixture prior, whose
+    # gradient is exactly zero (UniformDistribution.scala:78-81), so the posterior gradient IS the likelihood's.
+    post = t.UnnormalisedPosterior([t.UniformPrior.fromBounds("foo", [5, 5], [-5, -5])],
+                                   [t.GaussianLinearLikelihood.of(f["A"], f["y"], f["ci"], "foo")], kernelPath=path)
+    assert np.array_equal(post.logPdfGradientAt({"foo": [1, 2]})["foo"], [0.0, 0.0])          # :36-38
+    assert np.array_equal(post.logPdfGradientAt({"foo": [3, 2]})["foo"], [-4e5, -8.8e5])      # :45-47
+    lv = -2 * math.log(10.0)
+    d = GOLDEN["derived"]
+    assert post.logPdfAt({"foo": [1, 2]}) == pytest.approx(d["foo_likelihood_logpdf_at_1_2"] + lv, rel=1e-13)
+    assert post.logPdfAt({"foo": [3, 2]}) == pytest.approx(d["foo_likelihood_logpdf_at_3_2"] + lv, rel=1e-13)
+
+
+@pytest.mark.parametrize("incremental", [False, True])
+def test_GaussianLikelihoodSpec_fd_gradient(incremental):
+    f = GOLDEN["foo_likelihood"]
+    fm = t.NonLinearForwardModel.of("identity", {"foo": f["A"]}, differential=f["fd_differential"],
+                                    domainDimensions={"foo": 2}, rangeDimension=2)
+    post = t.UnnormalisedPosterior([t.UniformPrior.fromBounds("foo", [5, 5], [-5, -5])],
+                                   [t.GaussianLikelihood(fm, f["y"], f["ci"])], fdIncremental=incremental)
+    assert np.array_equal(post.logPdfGradientAt({"foo": [1, 2]})["foo"], [0.0, 0.0])          # GaussianLikelihoodSpec:37-39
+    got = post.logPdfGradientAt({"foo": [3, 2]})["foo"]
+    assert np.max(np.abs(got - np.array([-4e5, -8.8e5]))) < f["fd_abs_tol"]                    # :46-48
+
+
+def test_fixture_posterior_values_and_label_order():
+    foo, bar = GOLDEN["foo_likelihood"], GOLDEN["bar_likelihood"]
+    priors = [t.GaussianPrior.fromConfidenceIntervals("foo", [1, 2], [3, 5]),
+              t.GaussianPrior.fromConfidenceIntervals("bar", [5], [0.1])]
+    liks = [t.GaussianLinearLikelihood.of(foo["A"], foo["y"], foo["ci"], "foo"),
+            t.GaussianLinearLikelihood.of(bar["A"], bar["y"], bar["ci"], "bar")]
+    post = t.UnnormalisedPosterior(priors, liks)
+    assert post.layout == {"bar": (0, 1), "foo": (1, 2)}                      # Posterior.scala:40-48
+    ref = o.Posterior([o.gaussian_prior_from_ci("foo", [1, 2], [3, 5]), o.gaussian_prior_from_ci("bar", [5], [0.1])],
+                      [o.gaussian_linear_likelihood(foo["A"], foo["y"], foo["ci"], "foo"),
+                       o.gaussian_linear_likelihood(bar["A"], bar["y"], bar["ci"], "bar")])
+    for x in ([5.0, 1.0, 2.0], [4.9, 3.0, 2.0], [5.2, -1.0, 0.5]):
+        params = {"bar": x[:1], "foo": x[1:]}
+        assert post.logPdfAt(params) == pytest.approx(ref.log_pdf(np.array(x)), rel=TOL)
+        g = post.logPdfGradientAt(params)
+        want = ref.log_pdf_gradient(np.array(x))
+        got = np.concatenate([g["bar"], g["foo"]])
+        assert rel_err_grad(got[None], want[None]) < TOL
+
+
+def test_uniform_prior_half_open_and_minus_inf():
+    post = t.UnnormalisedPosterior([t.UniformPrior.fromBounds("u", [5, 5], [-5, -5])])
+    lp = post.logPdfBatch([[0, 0], [-5, 0], [5, 0], [0, 4.999999], [0, np.nan]])
+    assert lp[0] == pytest.approx(-2 * math.log(10)) and lp[1] == lp[0] and lp[3] == lp[0]
+    assert lp[2] == -math.inf and lp[4] == -math.inf                          # UniformDistribution.scala:61-76
+    _, g = post.logPdfGradBatch([[0, 0], [7, 0]])
+    assert np.array_equal(g, np.zeros((2, 2)))
+
+
+# ---- random linear-Gaussian models: every kernel path vs the oracle ---------------------------------------
+SHAPES = [(1, 1, 1), (2, 2, 3), (3, 5, 7), (8, 32, 64), (10, 1000, 65), (12, 200, 96), (17, 333, 130),
+          (24, 100, 1), (33, 257, 200), (50, 50, 129), (56, 640, 64), (80, 500, 70), (100, 1000, 256), (128, 300, 100)]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("d,n,B", SHAPES)
+def test_linear_gaussian_random(path, d, n, B):
+    prob = linear_gaussian_problem(d, n, seed=1000 + d * 7 + n)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")],
+                                   kernelPath=path)
+    rng = np.random.default_rng(d + n + B)
+    for X in (typical_set_points(prob, B, seed=B) if n >= d else rng.standard_normal((B, d)),
+              prob["pm"] + 10.0 * rng.standard_normal((B, d))):               # typical set and prior far field
+        want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
+                                                  prior_var=prob["pvar"])
+        lp, g = post.logPdfGradBatch(X)
+        assert rel_err_logp(lp, want_lp) < TOL
+        assert rel_err_grad(g, want_g) < TOL
+        lp_only = post.logPdfBatch(X)
+        assert np.array_equal(lp_only, lp) or rel_err_logp(lp_only, want_lp) < TOL
+    assert post.lastKernelPath == ("generic" if path == capi.KERNEL_GENERIC else "fused_dmma")
+
+
+def test_literal_dense_reference_agrees_at_small_size():
+    """The literal restatement (dense covariance, LU solve per logPdf) vs the CUDA path, one point at a time."""
+    prob = linear_gaussian_problem(6, 40, seed=5)
+    ref = o.Posterior([o.gaussian_prior_from_ci("theta", prob["pm"], prob["pci"])],
+                      [o.gaussian_linear_likelihood(prob["A"], prob["y"], prob["ci"], "theta")])
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
+    X = typical_set_points(prob, 9, seed=1)
+    lp, g = post.logPdfGradBatch(X)
+    for b in range(X.shape[0]):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_multi_label_blocks_offset_and_two_likelihoods(path):
+    rng = np.random.default_rng(11)
+    n1, n2 = 70, 45
+    dims = {"alpha": 3, "beta": 5, "gamma": 2}
+    A1 = {"gamma": rng.standard_normal((n1, 2)), "alpha": rng.standard_normal((n1, 3))}      # skips beta: non-contiguous
+    A2 = {"beta": rng.standard_normal((n2, 5))}
+    off = rng.standard_normal(n1)
+    y1, y2 = rng.standard_normal(n1), rng.standard_normal(n2)
+    ci1, ci2 = rng.uniform(0.1, 2, n1), rng.uniform(0.1, 2, n2)
+    cov = np.array([[2.0, 0.3], [0.3, 1.0]])
+    priors = [t.GaussianPrior.fromConfidenceIntervals("beta", rng.standard_normal(5), rng.uniform(1, 3, 5)),
+              t.UniformPrior.fromBounds("alpha", [4, 4, 4], [-4, -4, -4]),
+              t.GaussianPrior.fromCovarianceMatrix("gamma", [0.5, -0.5], cov)]
+    liks = [t.GaussianLikelihood(t.LinearForwardModel.of(transform=A1, vectorOffset=off), y1, ci1),
+            t.GaussianLinearLikelihood.of(A2["beta"], y2, ci2, "beta")]
+    post = t.UnnormalisedPosterior(priors, liks, kernelPath=path)
+    ref = o.Posterior([o.gaussian_prior_from_ci("beta", priors[0].a, priors[0].b),
+                       o.uniform_prior_from_bounds("alpha", [4, 4, 4], [-4, -4, -4]),
+                       o.gaussian_prior_from_cov("gamma", [0.5, -0.5], cov)],
+                      [o.gaussian_likelihood(o.LinearForwardModel(A1, off), y1, ci1),
+                       o.gaussian_linear_likelihood(A2["beta"], y2, ci2, "beta")])
+    assert post.layout == {"alpha": (0, 3), "beta": (3, 5), "gamma": (8, 2)}
+    X = rng.uniform(-3.9, 3.9, (37, 10))
+    X[5, 1] = 4.5                                                              # outside the uniform box
+    lp, g = post.logPdfGradBatch(X)
+    for b in range(X.shape[0]):
+        want = ref.log_pdf(X[b])
+        if math.isinf(want):
+            assert lp[b] == -math.inf
+        else:
+            assert lp[b] == pytest.approx(want, rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("faithful", [True, False])
+def test_cauchy_linear_likelihood_and_prior(path, faithful):
+    rng = np.random.default_rng(3)
+    d, n, B = 7, 60, 33
+    A = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    ci = rng.uniform(0.5, 2.0, n)
+    pm, pci = rng.standard_normal(d), rng.uniform(1, 3, d)
+    post = t.UnnormalisedPosterior([t.CauchyPrior("c", pm, pci)], [t.CauchyLikelihood.of(A, y, ci, "c")],
+                                   cauchyReferenceSign=faithful, kernelPath=path)
+    ref = o.Posterior([o.cauchy_prior("c", pm, pci, faithful)],
+                      [o.cauchy_likelihood(o.LinearForwardModel({"c": A}), y, ci, faithful)])
+    X = rng.standard_normal((B, d))
+    lp, g = post.logPdfGradBatch(X)
+    for b in range(B):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+@pytest.mark.parametrize("link", ["tanh", "exp", "square", "softplus", "sigmoid"])
+@pytest.mark.parametrize("dist", ["gaussian", "cauchy"])
+def test_nonlinear_analytic_jacobian(link, dist):
+    rng = np.random.default_rng(21)
+    d, n, B = 9, 50, 20
+    A = rng.standard_normal((n, d)) / 3
+    off = 0.1 * rng.standard_normal(n)
+    fn = {"tanh": np.tanh, "exp": np.exp, "square": np.square, "softplus": lambda z: np.logaddexp(0, z),
+          "sigmoid": lambda z: 1 / (1 + np.exp(-z))}[link]
+    dfn = {"tanh": lambda z: 1 - np.tanh(z) ** 2, "exp": np.exp, "square": lambda z: 2 * z,
+           "softplus": lambda z: 1 / (1 + np.exp(-z)), "sigmoid": lambda z: fn(z) * (1 - fn(z))}[link]
+    y = fn(A @ rng.standard_normal(d) + off) + 0.05 * rng.standard_normal(n)
+    ci = np.full(n, 0.1)
+    pm, pci = np.zeros(d), np.full(d, 4.0)
+    fm = t.NonLinearForwardModel.of(link, {"w": A}, vectorOffset=off)
+    lk = t.GaussianLikelihood(fm, y, ci) if dist == "gaussian" else t.CauchyLikelihood(fm, y, ci)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", pm, pci)], [lk], cauchyReferenceSign=False)
+    ofm = o.NonLinearForwardModel(lambda p: fn(A @ p["w"] + off), None, {"w": d}, n,
+                                  jacobian=lambda p: {"w": dfn(A @ p["w"] + off)[:, None] * A})
+    olk = o.gaussian_likelihood(ofm, y, ci) if dist == "gaussian" else o.cauchy_likelihood(ofm, y, ci, False)
+    ref = o.Posterior([o.gaussian_prior_from_ci("w", pm, pci)], [olk])
+    X = 0.5 * rng.standard_normal((B, d))
+    lp, g = post.logPdfGradBatch(X)
+    for b in range(B):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+@pytest.mark.parametrize("incremental", [False, True])
+def test_nonlinear_fd_jacobian_matches_reference_fd(incremental):
+    """FiniteDifferenceJacobian.scala:30-55.  A forward difference divides rounding noise of size eps*|f| by h, so
+    two correct implementations that sum A.theta in different orders agree only to ~ sqrt(d) eps |f| / (h |J|);
+    the tolerance below states that bound (1e-7 at h = 1e-6), not 1e-10."""
+    rng = np.random.default_rng(5)
+    d, n, B = 20, 64, 16
+    h = 1e-6
+    A = rng.standard_normal((n, d)) / np.sqrt(d)
+    y = np.tanh(A @ rng.standard_normal(d)) + 0.05 * rng.standard_normal(n)
+    ci = np.full(n, 0.1)
+    pm, pci = np.zeros(d), np.full(d, 4.0)
+    fm = t.NonLinearForwardModel.of("tanh", {"w": A}, differential=h)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", pm, pci)],
+                                   [t.CauchyLikelihood(fm, y, ci)], cauchyReferenceSign=True, fdIncremental=incremental)
+    ofm = o.NonLinearForwardModel(lambda p: np.tanh(A @ p["w"]), h, {"w": d}, n)
+    ref = o.Posterior([o.gaussian_prior_from_ci("w", pm, pci)], [o.cauchy_likelihood(ofm, y, ci, True)])
+    X = 0.5 * rng.standard_normal((B, d))
+    lp, g = post.logPdfGradBatch(X)
+    for b in range(B):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < 1e-7
+
+
+def test_uniform_likelihood():
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((5, 3))
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("a", [0, 0, 0], [2, 2, 2])],
+                                   [t.UniformLikelihood(t.LinearForwardModel.of("a", A), np.full(5, 1.0), np.full(5, -1.0))])
+    ref = o.Posterior([o.gaussian_prior_from_ci("a", [0, 0, 0], [2, 2, 2])],
+                      [o.Likelihood(o.LinearForwardModel({"a": A}), o.UniformDistribution(np.full(5, 1.0), np.full(5, -1.0)))])
+    X = 0.6 * rng.standard_normal((64, 3))
+    lp, g = post.logPdfGradBatch(X)
+    n_in = 0
+    for b in range(64):
+        want = ref.log_pdf(X[b])
+        if math.isinf(want):
+            assert lp[b] == -math.inf
+        else:
+            n_in += 1
+            assert lp[b] == pytest.approx(want, rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+    assert 0 < n_in < 64
+
+
+def test_empty_batch_and_ragged_tail():
+    prob = linear_gaussian_problem(10, 100, seed=2)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
+    assert post.logPdfBatch(np.zeros((0, 10))).shape == (0,)
+    for B in (1, 7, 63, 64, 65, 127, 129, 1000):
+        X = typical_set_points(prob, B, seed=B)
+        want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
+                                                  prior_var=prob["pvar"])
+        lp, g = post.logPdfGradBatch(X)
+        assert rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
+
+
+def test_run_to_run_determinism():
+    prob = linear_gaussian_problem(40, 3000, seed=8)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
+    X = typical_set_points(prob, 700, seed=3)
+    a = post.logPdfGradBatch(X)
+    b = post.logPdfGradBatch(X)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 (100-d, 10k observations, 4096 chains): oracle parity on a slice, plus size-independent
+    properties on the whole batch -- the gradient vanishes at the analytic posterior mean, and
+    logp(x) - logp(mu) = -1/2 (x-mu)^T Lambda (x-mu) (exact for a Gaussian posterior)."""
+    prob = linear_gaussian_problem(100, 10_000, seed=20260102)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
+    X = typical_set_points(prob, 4096, seed=4)
+    lp, g = post.logPdfGradBatch(X)
+    assert post.lastKernelPath == "fused_dmma"
+    want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
+                                              prior_var=prob["pvar"])
+    assert rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
+    mean, cov = o.analytic_gaussian_posterior(prob["pm"], prob["pvar"], prob["A"], prob["y"], prob["var"])
+    lam = np.linalg.inv(cov)
+    lp0, g0 = post.logPdfGradBatch(mean[None, :])
+    gscale = np.max(np.abs(g))
+    assert np.max(np.abs(g0)) < 1e-9 * gscale                                 # stationary point
+    D = X - mean[None, :]
+    quad = -0.5 * np.einsum("bi,ij,bj->b", D, lam, D)
+    assert np.max(np.abs((lp - lp0[0]) - quad)) < 1e-9 * np.max(np.abs(quad)) + 1e-7
+    assert np.max(np.abs(g + D @ lam)) < 1e-9 * gscale                        # grad = -Lambda (x - mu)

@@ -1,0 +1,12 @@
+"""thylacine_b200 -- B200-native (sm_100a) posterior-evaluation hot path behind the reference's API surface.
+
+Only what the hot path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of
+``include/thylacine_b200.h``), ``_capi`` (ctypes binding) and ``api`` (host-side mirror of the
+reference's Scala classes).  There is no CPU fallback.
+"""
+from ._capi import ThylacineError, lib  # noqa: F401
+from . import _capi as capi  # noqa: F401
+from .api import (  # noqa: F401
+    CauchyLikelihood, CauchyPrior, GaussianLikelihood, GaussianLinearLikelihood, GaussianPrior, LinearForwardModel,
+    NonLinearForwardModel, UniformLikelihood, UniformPrior, UnnormalisedPosterior, kernelLaunchCount,
+)

@@ -1,0 +1,88 @@
+// Batched evaluation of the posterior sum: Posterior.logPdfAt / logPdfGradientAt for B points at once.
+//   /root/reference/src/main/scala/thylacine/model/components/posterior/Posterior.scala:50-73
+// Order: priors initialise logp / grad, then each likelihood term adds its contribution (the reference sums
+// priors first, likelihoods after, left to right -- SURVEY Q7).
+#include "kernels.h"
+
+namespace thy {
+
+thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign) {
+  if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
+  if (B < 0) return fail(THY_ERR_INVALID_ARGUMENT, "negative batch size");
+  if (B == 0) return THY_OK;
+  if (!X || !logp) return fail(THY_ERR_INVALID_ARGUMENT, "null device pointer");
+  const double csign = (cauchy_correct_sign || !m->opt_cauchy_ref_sign) ? -1.0 : 1.0;
+  cudaStream_t s = m->stream;
+  THY_TRY(launch_prior(m->prior_view, B, X, logp, grad, csign, s));
+  for (auto& own : m->lik_dev) {
+    const LikDev& lk = own->view;
+    const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&
+                         lk.distribution != THY_DIST_UNIFORM);
+    int path = m->opt_kernel_path;
+    if (path == 2 && !(linear && fused_dmma_supported(lk, grad != nullptr)))
+      return fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
+    if (path == 3 && !(linear && stream_supported(lk, B)))
+      return fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
+    if (path == 0) {
+      if (linear && stream_supported(lk, B) && B <= 16)
+        path = 3;
+      else if (linear && fused_dmma_supported(lk, grad != nullptr))
+        path = 2;
+      else
+        path = 1;
+    }
+    if (path == 2) {
+      m->last_path = "fused_dmma";
+      THY_TRY(launch_fused_dmma(m, *own, B, X, logp, grad, csign, s));
+    } else if (path == 3) {
+      m->last_path = "stream";
+      THY_TRY(launch_stream(m, *own, B, X, logp, grad, csign, s));
+    } else {
+      m->last_path = "generic";
+      THY_TRY(launch_generic_likelihood(m, *own, B, X, logp, grad, csign, s));
+    }
+  }
+  if (m->lik_dev.empty()) m->last_path = "priors_only";
+  return THY_OK;
+}
+
+static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad) {
+  if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
+  THY_TRY(require_device());
+  if (B < 0) return fail(THY_ERR_INVALID_ARGUMENT, "negative batch size");
+  if (B == 0) return THY_OK;
+  if (!X || !out_logp) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  const size_t nx = (size_t)B * m->d;
+  THY_TRY(m->ws.X.reserve(nx));
+  THY_TRY(m->ws.logp.reserve((size_t)B));
+  if (out_grad) THY_TRY(m->ws.grad.reserve(nx));
+  cudaStream_t s = m->stream;
+  THY_CUDA_CHECK(cudaMemcpyAsync(m->ws.X.ptr, X, nx * sizeof(double), cudaMemcpyHostToDevice, s));
+  THY_TRY(eval_batch_dev(m, B, m->ws.X.ptr, m->ws.logp.ptr, out_grad ? m->ws.grad.ptr : nullptr, false));
+  THY_CUDA_CHECK(cudaMemcpyAsync(out_logp, m->ws.logp.ptr, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (out_grad) THY_CUDA_CHECK(cudaMemcpyAsync(out_grad, m->ws.grad.ptr, nx * sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  return THY_OK;
+}
+
+}  // namespace thy
+
+using namespace thy;
+
+extern "C" {
+
+thy_status thy_logpdf_batch(thy_model_t m, int64_t B, const double* X, double* out_logp) {
+  return eval_host(m, B, X, out_logp, nullptr);
+}
+
+thy_status thy_logpdf_grad_batch(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad) {
+  if (!out_grad) return fail(THY_ERR_INVALID_ARGUMENT, "null gradient pointer");
+  return eval_host(m, B, X, out_logp, out_grad);
+}
+
+thy_status thy_logpdf_grad_batch_dev(thy_model_t m, int64_t B, const double* X_dev, double* logp_dev, double* grad_dev) {
+  THY_TRY(require_device());
+  return eval_batch_dev(m, B, X_dev, logp_dev, grad_dev, false);
+}
+
+}  // extern "C"

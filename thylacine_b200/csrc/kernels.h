@@ -1,0 +1,48 @@
+// Kernel launchers shared between translation units.
+#pragma once
+#include "model.h"
+
+namespace thy {
+
+// terms.cu -- priors (initialises logp / grad), warp-shuffle reductions
+thy_status launch_prior(const PriorDev& pr, int64_t B, const double* X, double* logp, double* grad, double cauchy_sign,
+                        cudaStream_t s);
+
+// kernels_generic.cu -- any link / distribution / jacobian mode, any shape (tiled DFMA GEMMs, W materialised)
+thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp,
+                                     double* grad, double cauchy_sign, cudaStream_t s);
+
+// kernels_fused_dmma.cu -- linear forward model + Gaussian/Cauchy observations, fused forward/residual/adjoint
+int fused_nt_for(int dl);  // 0 when the width is not covered by the fused kernel
+bool fused_dmma_supported(const LikDev& lik, bool want_grad);
+thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
+                             double cauchy_sign, cudaStream_t s);
+
+// kernels_stream.cu -- small-batch memory-bound pass (A streamed once per batch)
+bool stream_supported(const LikDev& lik, int64_t B);
+thy_status launch_stream(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
+                         double cauchy_sign, cudaStream_t s);
+
+// link functions (device), shared by the generic and FD kernels
+__device__ __forceinline__ double link_eval(int link, double z) {
+  switch (link) {
+    case THY_LINK_TANH: return tanh(z);
+    case THY_LINK_EXP: return exp(z);
+    case THY_LINK_SQUARE: return z * z;
+    case THY_LINK_SOFTPLUS: return z > 0 ? z + log1p(exp(-z)) : log1p(exp(z));
+    case THY_LINK_SIGMOID: return 1.0 / (1.0 + exp(-z));
+    default: return z;
+  }
+}
+__device__ __forceinline__ double link_deriv(int link, double z) {
+  switch (link) {
+    case THY_LINK_TANH: { double t = tanh(z); return 1.0 - t * t; }
+    case THY_LINK_EXP: return exp(z);
+    case THY_LINK_SQUARE: return 2.0 * z;
+    case THY_LINK_SOFTPLUS: return 1.0 / (1.0 + exp(-z));
+    case THY_LINK_SIGMOID: { double s = 1.0 / (1.0 + exp(-z)); return s * (1.0 - s); }
+    default: return 1.0;
+  }
+}
+
+}  // namespace thy

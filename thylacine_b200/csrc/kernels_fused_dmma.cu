@@ -1,0 +1,358 @@
+// Fused linear forward / weighted residual / adjoint kernel on the fp64 tensor cores (DMMA.8x8x4), sm_100a.
+//
+// What it computes, per chain b (reference: model/components/likelihood/Likelihood.scala:43-65 with
+// forwardmodel/LinearForwardModel.scala:103-114 and distributions/GaussianDistribution.scala:52-68 or
+// CauchyDistribution.scala:51-79; paths relative to /root/reference/src/main/scala/thylacine/):
+//     f = A x_b (+ offset);  r = y - f;  w = r / var;  q_b = sum_i r_i w_i;  G_b = A^T w
+//     Gaussian: logp += -q/2 + const,          grad += G
+//     Cauchy  : logp += c - (1+n)/2 log(1+q),  grad += -sign (1+n)/(1+q) G   (scalar per chain, so it factors out)
+//
+// Structure (FlashAttention-like chained GEMMs, A plays both K and V):
+//   * one warp owns 8 chains; X^T fragments (8 chains x d) and the G^T accumulators (8 chains x d) live in registers;
+//   * A is streamed through shared memory in blocks of MB = 32 observation rows by a dedicated producer warp using
+//     1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a STAGES-deep mbarrier ring;
+//   * GEMM1  Z^T[8 x 8 obs] = X^T[8 x d] . A_blk^T    (K = d):   B fragment read straight from the A tile;
+//   * epilogue in registers: r, w, q -- the GEMM1 C fragment IS the GEMM2 A fragment (no shuffle, no smem round trip)
+//     because the contraction index of GEMM2 may be permuted freely: the 8 observation columns of a C tile are
+//     assigned to rows pi = [0,1,2,3,5,4,7,6] of the A tile, which together with a row pitch = 4 (mod 8) doubles makes
+//     every fragment load of both GEMMs bank-conflict free;
+//   * GEMM2  G^T[8 x d] += W^T[8 x 8 obs] . A_blk     (K = 8 obs, two k4 steps);
+//   * persistent grid (one CTA per SM), stream-K split of the (chain tile, row block) space so every SM gets the same
+//     number of row blocks; tiles split across CTAs go through partial buffers and a deterministic finish kernel,
+//     tiles owned by one CTA are finished in-kernel.
+// Z = A X (n x B, 328 MB at the 100-d / 10k-obs / 4096-chain config) is never materialised.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace thy {
+
+namespace {
+
+constexpr int NW = 8;        // consumer warps per CTA (8 chains each)
+constexpr int TILE_B = 64;   // chains per tile
+constexpr int MB = 32;       // observation rows per pipeline stage
+constexpr int JG = MB / 8;   // 8-row groups per stage
+
+__host__ __device__ inline long long unit_begin(long long c, long long U, long long G) { return (c * U) / G; }
+
+struct FusedParams {
+  const double* A;        // [n_pad][LDS]
+  const double2* yiv;     // [n_pad] (y - offset, 1/var)
+  const int* col;         // [dl]
+  const double* X;        // [B][d]
+  double* logp;           // [B]
+  double* grad;           // [B][d] or null
+  double* partG;          // [2G][TILE_B][NP]
+  double* partL;          // [2G][TILE_B]
+  long long B;
+  int d, dl, n, nblk;     // nblk = n_pad / MB
+  long long T, U;         // chain tiles, units
+  int stages;
+  int distribution;
+  double log_const, cauchy_sign;
+};
+
+template <int NT>
+struct Cfg {
+  static constexpr int NP = 8 * NT;       // padded columns
+  static constexpr int KS = 2 * NT;       // k4 steps of GEMM1
+  static constexpr int LDS = 8 * NT + 4;  // row pitch in doubles: 4 (mod 8) -> conflict-free fragments
+  static constexpr int A_BYTES = MB * LDS * 8;
+  static constexpr int Y_BYTES = MB * 16;
+  static constexpr int STAGE_BYTES = A_BYTES + Y_BYTES;
+};
+
+__device__ __forceinline__ double apply_logp(int distribution, double q, int n, double log_const) {
+  if (distribution == THY_DIST_GAUSSIAN) return -0.5 * q + log_const;
+  return log_const - (1.0 + n) / 2.0 * log(1.0 + q);
+}
+__device__ __forceinline__ double apply_scale(int distribution, double q, int n, double cauchy_sign) {
+  if (distribution == THY_DIST_GAUSSIAN) return 1.0;
+  return -cauchy_sign * (1.0 + n) / (1.0 + q);
+}
+
+template <int NT, bool WANT_GRAD>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedParams p) {
+  using C = Cfg<NT>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + p.stages;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long G = gridDim.x;
+  const long long c = blockIdx.x;
+  const long long u0 = unit_begin(c, p.U, G), u1 = unit_begin(c + 1, p.U, G);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], NW);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ===== producer warp: one lane drives the TMA engine =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long u = u0; u < u1; ++u) {
+        const int blk = (int)(u % p.nblk);
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        unsigned char* dst = smem + (size_t)stage * C::STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        ptx::bulk_g2s(dst, p.A + (size_t)blk * MB * C::LDS, C::A_BYTES, &full_bar[stage]);
+        ptx::bulk_g2s(dst + C::A_BYTES, p.yiv + (size_t)blk * MB, C::Y_BYTES, &full_bar[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int g8 = lane >> 2;  // row within the 8-chain group / column within an 8-wide B fragment
+  const int q4 = lane & 3;   // k index inside a k4 step
+  // observation-row permutation pi = [0,1,2,3,5,4,7,6]
+  const int pi_g = (g8 < 4) ? g8 : (g8 ^ 1);
+  const int pi_s0 = (q4 < 2) ? (2 * q4) : (2 * q4 + 1);      // pi(2q)   = 0,2,5,7
+  const int pi_s1 = (q4 < 2) ? (2 * q4 + 1) : (2 * q4);      // pi(2q+1) = 1,3,4,6
+  const int off1 = pi_g * C::LDS + q4;                        // GEMM1 B fragment: A_s[pi(g)][4kk + q]
+  const int off2_s0 = pi_s0 * C::LDS + g8;                    // GEMM2 B fragment: A_s[pi(2q+s)][8g' + g]
+  const int off2_s1 = pi_s1 * C::LDS + g8;
+
+  double xf[C::KS];
+  double ga[WANT_GRAD ? NT : 1][2];
+  double ssq = 0.0;
+  long long cur_tile = -1;
+  long long seg_begin = 0;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  auto flush = [&](long long tile, long long ub, long long ue) {
+    // segment [ub, ue) of `tile` is complete
+    const double qsum = quad_sum(ssq);
+    const long long chain = tile * TILE_B + warp * 8 + g8;
+    const bool full_tile = (ue - ub) == p.nblk;
+    if (full_tile) {
+      if (chain < p.B) {
+        if (q4 == 0) p.logp[chain] += apply_logp(p.distribution, qsum, p.n, p.log_const);
+        if (WANT_GRAD) {
+          const double sc = apply_scale(p.distribution, qsum, p.n, p.cauchy_sign);
+          double* grow = p.grad + chain * p.d;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const int j = 8 * t + 2 * q4;
+            if (j < p.dl) grow[p.col[j]] += sc * ga[WANT_GRAD ? t : 0][0];
+            if (j + 1 < p.dl) grow[p.col[j + 1]] += sc * ga[WANT_GRAD ? t : 0][1];
+          }
+        }
+      }
+    } else {
+      // partial segment: slot 2c for the CTA's first segment, 2c+1 otherwise
+      const long long slot = 2 * c + ((ub == u0) ? 0 : 1);
+      const int row = warp * 8 + g8;
+      if (q4 == 0) p.partL[slot * TILE_B + row] = qsum;
+      if (WANT_GRAD) {
+        double* prow = p.partG + ((size_t)slot * TILE_B + row) * C::NP;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          *reinterpret_cast<double2*>(prow + 8 * t + 2 * q4) = make_double2(ga[WANT_GRAD ? t : 0][0], ga[WANT_GRAD ? t : 0][1]);
+      }
+    }
+  };
+
+  for (long long u = u0; u < u1; ++u) {
+    const long long tile = u / p.nblk;
+    if (tile != cur_tile) {
+      if (cur_tile >= 0) flush(cur_tile, seg_begin, u);
+      cur_tile = tile;
+      seg_begin = u;
+      ssq = 0.0;
+      const long long chain = tile * TILE_B + warp * 8 + g8;
+#pragma unroll
+      for (int kk = 0; kk < C::KS; ++kk) {
+        const int k = 4 * kk + q4;
+        xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + p.col[k]] : 0.0;
+      }
+      if (WANT_GRAD) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) ga[t][0] = ga[t][1] = 0.0;
+      }
+    }
+
+    ptx::mbar_wait(&full_bar[stage], phase);
+    const double* As = reinterpret_cast<const double*>(smem + (size_t)stage * C::STAGE_BYTES);
+    const double2* Ys = reinterpret_cast<const double2*>(smem + (size_t)stage * C::STAGE_BYTES + C::A_BYTES);
+
+    // ---- GEMM1: Z^T = X^T A_blk^T, JG independent accumulator chains ----
+    double z[JG][2];
+#pragma unroll
+    for (int j = 0; j < JG; ++j) z[j][0] = z[j][1] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < C::KS; ++kk) {
+#pragma unroll
+      for (int j = 0; j < JG; ++j) {
+        const double bfrag = As[off1 + j * 8 * C::LDS + 4 * kk];
+        ptx::dmma884(z[j][0], z[j][1], xf[kk], bfrag);
+      }
+    }
+    // ---- epilogue: residual, weight, quadratic form; C fragment -> A fragment of GEMM2 ----
+#pragma unroll
+    for (int j = 0; j < JG; ++j) {
+      const double2 y0 = Ys[j * 8 + pi_s0];
+      const double2 y1 = Ys[j * 8 + pi_s1];
+      const double r0 = y0.x - z[j][0];
+      const double r1 = y1.x - z[j][1];
+      const double w0 = r0 * y0.y;
+      const double w1 = r1 * y1.y;
+      ssq = fma(r0, w0, ssq);
+      ssq = fma(r1, w1, ssq);
+      z[j][0] = w0;
+      z[j][1] = w1;
+    }
+    // ---- GEMM2: G^T += W^T A_blk ----
+    if (WANT_GRAD) {
+#pragma unroll
+      for (int j = 0; j < JG; ++j) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const double b0 = As[off2_s0 + j * 8 * C::LDS + 8 * t];
+          ptx::dmma884(ga[t][0], ga[t][1], z[j][0], b0);
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const double b1 = As[off2_s1 + j * 8 * C::LDS + 8 * t];
+          ptx::dmma884(ga[t][0], ga[t][1], z[j][1], b1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+    if (++stage == p.stages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+  if (cur_tile >= 0) flush(cur_tile, seg_begin, u1);
+}
+
+// Finish: tiles split across several CTAs -- sum their partials in CTA order (deterministic) and apply.
+template <int NT>
+__global__ void __launch_bounds__(256) k_fused_finish(const FusedParams p, long long G) {
+  using C = Cfg<NT>;
+  const int lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const long long t = b / TILE_B;
+  const int row = (int)(b % TILE_B);
+  const long long ub = t * p.nblk, ue = ub + p.nblk;
+  // first CTA whose range contains unit ub, last CTA whose range contains unit ue-1
+  long long c_lo = (ub * G) / p.U;
+  while (c_lo > 0 && unit_begin(c_lo, p.U, G) > ub) --c_lo;
+  while (unit_begin(c_lo + 1, p.U, G) <= ub) ++c_lo;
+  long long c_hi = ((ue - 1) * G) / p.U;
+  while (c_hi > 0 && unit_begin(c_hi, p.U, G) > ue - 1) --c_hi;
+  while (unit_begin(c_hi + 1, p.U, G) <= ue - 1) ++c_hi;
+  if (c_lo == c_hi) return;  // whole tile owned by one CTA: finished in-kernel
+  double q = 0.0;
+  for (long long c = c_lo; c <= c_hi; ++c) {
+    const long long slot = 2 * c + ((unit_begin(c, p.U, G) >= ub) ? 0 : 1);
+    q += p.partL[slot * TILE_B + row];
+  }
+  if (lane == 0) p.logp[b] += apply_logp(p.distribution, q, p.n, p.log_const);
+  if (p.grad) {
+    const double sc = apply_scale(p.distribution, q, p.n, p.cauchy_sign);
+    for (int j = lane; j < p.dl; j += 32) {
+      double s = 0.0;
+      for (long long c = c_lo; c <= c_hi; ++c) {
+        const long long slot = 2 * c + ((unit_begin(c, p.U, G) >= ub) ? 0 : 1);
+        s += p.partG[((size_t)slot * TILE_B + row) * C::NP + j];
+      }
+      p.grad[b * p.d + p.col[j]] += sc * s;
+    }
+  }
+}
+
+template <int NT>
+thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_t s) {
+  using C = Cfg<NT>;
+  const int G = sm_count();
+  int stages = (200 * 1024) / C::STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return fail(THY_ERR_UNSUPPORTED, "fused DMMA: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = (size_t)stages * C::STAGE_BYTES + 2 * stages * sizeof(uint64_t);
+  THY_TRY(m->ws.partG.reserve((size_t)2 * G * TILE_B * C::NP));
+  THY_TRY(m->ws.partL.reserve((size_t)2 * G * TILE_B));
+  p.partG = m->ws.partG.ptr;
+  p.partL = m->ws.partL.ptr;
+  if (want_grad) {
+    THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fused_dmma<NT, true><<<G, (NW + 1) * 32, smem, s>>>(p);
+  } else {
+    THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fused_dmma<NT, false><<<G, (NW + 1) * 32, smem, s>>>(p);
+  }
+  k_fused_finish<NT><<<(unsigned)ceil_div(p.B, 8), 256, 0, s>>>(p, G);
+  count_launch(2);
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
+}
+
+}  // namespace
+
+int fused_nt_for(int dl) {
+  static const int list[] = {1, 2, 3, 4, 5, 7, 10, 13, 16};
+  for (int nt : list)
+    if (8 * nt >= dl) return nt;
+  return 0;
+}
+
+bool fused_dmma_supported(const LikDev& lik, bool want_grad) {
+  (void)want_grad;
+  const int nt = fused_nt_for(lik.dl);
+  return nt > 0 && lik.lds == 8 * nt + 4 && lik.n_pad % MB == 0;
+}
+
+thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
+                             double cauchy_sign, cudaStream_t s) {
+  const LikDev& lk = lik.view;
+  FusedParams p{};
+  p.A = lk.A;
+  p.yiv = lk.yiv_lin;
+  p.col = lk.col;
+  p.X = X;
+  p.logp = logp;
+  p.grad = grad;
+  p.B = B;
+  p.d = m->d;
+  p.dl = lk.dl;
+  p.n = lk.n;
+  p.nblk = lk.n_pad / MB;
+  p.T = (B + TILE_B - 1) / TILE_B;
+  p.U = p.T * p.nblk;
+  p.distribution = lk.distribution;
+  p.log_const = lk.log_const;
+  p.cauchy_sign = cauchy_sign;
+  const bool wg = grad != nullptr;
+  switch (fused_nt_for(lk.dl)) {
+    case 1: return launch_nt<1>(m, p, wg, s);
+    case 2: return launch_nt<2>(m, p, wg, s);
+    case 3: return launch_nt<3>(m, p, wg, s);
+    case 4: return launch_nt<4>(m, p, wg, s);
+    case 5: return launch_nt<5>(m, p, wg, s);
+    case 7: return launch_nt<7>(m, p, wg, s);
+    case 10: return launch_nt<10>(m, p, wg, s);
+    case 13: return launch_nt<13>(m, p, wg, s);
+    case 16: return launch_nt<16>(m, p, wg, s);
+    default: return fail(THY_ERR_UNSUPPORTED, "fused DMMA: unsupported width");
+  }
+}
+
+}  // namespace thy

@@ -1,0 +1,114 @@
+// Host-side model description and the POD device views handed to kernels.
+#pragma once
+#include "common.cuh"
+#include <map>
+#include <memory>
+
+namespace thy {
+
+// ---- per-coordinate prior kinds (one prior owns each flat coordinate) -----------------------------
+enum PriorKind : int { PK_GAUSS_DIAG = 0, PK_UNIFORM = 1, PK_CAUCHY = 2, PK_GAUSS_FULL = 3 };
+
+struct PriorHost {
+  std::string label;
+  int dim = 0;
+  int kind = PK_GAUSS_DIAG;
+  std::vector<double> a;  // mean | upper bounds
+  std::vector<double> b;  // variances | lower bounds | dense covariance (dim*dim)
+  int offset = -1;        // position in the flat vector, assigned at finalize
+};
+
+struct LikelihoodHost {
+  int distribution = 0, link = 0, jacobian = 0, n = 0;
+  double differential = 0.0;
+  std::vector<std::string> labels;
+  std::vector<int> dims;
+  std::vector<std::vector<double>> blocks;
+  bool has_offset = false;
+  std::vector<double> offset, meas, unc;
+};
+
+// Cauchy and full-covariance Gaussian priors need a per-block reduction / mat-vec.
+struct SpecialTermDev {
+  int kind;          // PK_CAUCHY or PK_GAUSS_FULL
+  int offset, dim;
+  double log_mult;   // Cauchy: logMultiplier; full Gaussian: -(dim/2 log 2pi + sum log diag chol)
+  double grad_sign;  // Cauchy: +1 reference-faithful (Q3), -1 correct; full Gaussian: unused
+  const double* precision;  // full Gaussian: dim*dim row-major inverse covariance (device)
+};
+
+struct PriorDev {
+  int d;
+  const int* kind;     // [d]
+  const double* p0;    // [d] mean | lower
+  const double* p1;    // [d] inverse variance | upper
+  int n_special;
+  const SpecialTermDev* special;
+  double log_const;    // sum over diagonal-Gaussian normalisers and uniform -log V
+};
+
+struct LikDev {
+  int distribution, link, jacobian;
+  int n, dl;              // observations; compact domain width (columns this forward model reads)
+  int n_pad, lds;         // rows padded to a multiple of 32; row pitch (doubles), lds % 16 in {4, 12}
+  const double* A;        // [n_pad][lds], zero padded
+  const double2* yiv;     // [n_pad] (y, 1/var); Uniform: (upper, lower); padded rows (0, 0)
+  const double2* yiv_lin; // [n_pad] (y - offset, 1/var) for the linear fast paths
+  const double* off;      // [n_pad] vectorOffset (0 when absent)
+  const int* col;         // [dl] flat index of compact column k
+  double log_const;       // Gaussian: -(n/2 log 2pi + sum log sqrt(var)); Cauchy: logMultiplier; Uniform: -log V
+  double differential;
+  double cauchy_sign;     // +1 reference-faithful, -1 correct
+};
+
+struct LikDevOwner {
+  LikDev view{};
+  DevBuf<double> A, off;
+  DevBuf<double2> yiv, yiv_lin;
+  DevBuf<int> col;
+  std::vector<int> col_host;
+  bool contiguous = false;  // columns are a contiguous flat range starting at col[0]
+};
+
+struct Workspace {  // grow-only scratch owned by the model, reused across evaluations
+  DevBuf<double> X, logp, grad;         // staging for the host-pointer API
+  DevBuf<double> W;                     // generic path: weighted residuals [B][n_pad]
+  DevBuf<double> partG, partL;          // stream-K partial tiles
+  DevBuf<double> Z;                     // generic path scratch
+};
+
+}  // namespace thy
+
+struct thy_model_s {
+  std::vector<thy::PriorHost> priors;
+  std::vector<thy::LikelihoodHost> liks;
+  bool finalized = false;
+  int d = 0;
+  int opt_cauchy_ref_sign = 1;
+  int opt_fd_incremental = 0;
+  int opt_kernel_path = 0;
+  cudaStream_t stream = 0;
+  int device = -1;
+  std::map<std::string, std::pair<int, int>> layout;  // label -> (offset, dim)
+  // device state
+  thy::PriorDev prior_view{};
+  thy::DevBuf<int> pr_kind;
+  thy::DevBuf<double> pr_p0, pr_p1;
+  thy::DevBuf<thy::SpecialTermDev> pr_special;
+  std::vector<std::unique_ptr<thy::DevBuf<double>>> pr_precisions;
+  std::vector<std::unique_ptr<thy::LikDevOwner>> lik_dev;
+  thy::Workspace ws;
+  const char* last_path = "none";
+  // host copies kept for prior sampling
+  std::vector<int> h_kind;
+  std::vector<double> h_p0, h_p1;
+  std::vector<thy::SpecialTermDev> h_special;
+  std::vector<std::vector<double>> h_chol;  // per special term: lower Cholesky factor (dim*dim), row-major
+  thy::DevBuf<double> pr_chol;              // concatenated Cholesky factors of full-covariance priors
+  std::vector<int> h_chol_off;
+};
+
+namespace thy {
+// eval.cu
+thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false);
+}
