@@ -316,6 +316,12 @@ class UnnormalisedPosterior:
     def logPdfGradBatchDevice(self, B: int, x_ptr: int, logp_ptr: int, grad_ptr: Optional[int]) -> None:
         check(self._lib.thy_logpdf_grad_batch_dev(self._h, B, x_ptr, logp_ptr, grad_ptr))
 
+    def samplePriors(self, B: int = 1, seed: int = 0) -> np.ndarray:
+        """Posterior.samplePriors (Posterior.scala:64-65), B independent draws -> (B, d)."""
+        out = np.empty((B, self.domainDimension))
+        check(self._lib.thy_sample_priors(self._h, B, seed, _ptr(out)))
+        return out
+
     def setStream(self, cuda_stream: int) -> None:
         check(self._lib.thy_model_set_stream(self._h, cuda_stream))
 

@@ -351,6 +351,7 @@ thy_status thy_model_finalize(thy_model_t m) {
   THY_TRY(m->pr_p1.upload(m->h_p1));
   THY_TRY(m->pr_special.upload(m->h_special));
   THY_TRY(m->pr_chol.upload(chol_all));
+  THY_TRY(m->pr_chol_off.upload(m->h_chol_off));
   m->prior_view.d = d;
   m->prior_view.kind = m->pr_kind.ptr;
   m->prior_view.p0 = m->pr_p0.ptr;

@@ -106,9 +106,12 @@ struct thy_model_s {
   std::vector<std::vector<double>> h_chol;  // per special term: lower Cholesky factor (dim*dim), row-major
   thy::DevBuf<double> pr_chol;              // concatenated Cholesky factors of full-covariance priors
   std::vector<int> h_chol_off;
+  thy::DevBuf<int> pr_chol_off;
 };
 
 namespace thy {
 // eval.cu
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false);
+// sampling.cu
+thy_status sample_priors_dev(thy_model_s* m, int64_t B, uint64_t seed, double* X);
 }
