@@ -147,6 +147,11 @@ thy_status thy_sample_priors_dev(thy_model_t m, int64_t B, uint64_t rng_seed, do
 /* Name of the kernel path the last evaluation on this model used ("fused_dmma", "stream", "generic", ...). */
 const char* thy_model_last_kernel_path(thy_model_t m);
 
+/* Measurement hook: when enabled, a CUDA-event pair is recorded on the model's stream around the dominant kernel of
+ * every evaluation; thy_model_kernel_time synchronises, returns the summed duration and launch count, and resets. */
+thy_status thy_model_enable_timing(thy_model_t m, int enable);
+thy_status thy_model_kernel_time(thy_model_t m, double* out_total_ms, int64_t* out_launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,8 @@ SIGNATURES = {
     "thy_logpdf_grad_batch": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "thy_logpdf_grad_batch_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "thy_model_last_kernel_path": (C.c_char_p, [_vp]),
+    "thy_model_enable_timing": (C.c_int, [_vp, C.c_int]),
+    "thy_model_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "thy_sample_priors": (C.c_int, [_vp, C.c_int64, C.c_uint64, _dp]),
     "thy_sample_priors_dev": (C.c_int, [_vp, C.c_int64, C.c_uint64, _vp]),
 }

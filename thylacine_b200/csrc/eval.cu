@@ -85,4 +85,29 @@ thy_status thy_logpdf_grad_batch_dev(thy_model_t m, int64_t B, const double* X_d
   return eval_batch_dev(m, B, X_dev, logp_dev, grad_dev, false);
 }
 
+thy_status thy_model_enable_timing(thy_model_t m, int enable) {
+  if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
+  m->timing = enable != 0;
+  return THY_OK;
+}
+
+thy_status thy_model_kernel_time(thy_model_t m, double* out_total_ms, int64_t* out_launches) {
+  if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
+  double total = 0.0;
+  int64_t n = 0;
+  for (auto& ev : m->timing_events) {
+    float ms = 0.f;
+    THY_CUDA_CHECK(cudaEventSynchronize(ev.second));
+    THY_CUDA_CHECK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    total += ms;
+    ++n;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  m->timing_events.clear();
+  if (out_total_ms) *out_total_ms = total;
+  if (out_launches) *out_launches = n;
+  return THY_OK;
+}
+
 }  // extern "C"

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(256) k_fused_finish(const FusedParams p, long 
   if (c_lo == c_hi) return;  // whole tile owned by one CTA: finished in-kernel
   double q = 0.0;
   for (long long c = c_lo; c <= c_hi; ++c) {
+    if (unit_begin(c, p.U, G) == unit_begin(c + 1, p.U, G)) continue;  // CTA without work wrote nothing
     const long long slot = 2 * c + ((unit_begin(c, p.U, G) >= ub) ? 0 : 1);
     q += p.partL[slot * TILE_B + row];
   }
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(256) k_fused_finish(const FusedParams p, long 
     for (int j = lane; j < p.dl; j += 32) {
       double s = 0.0;
       for (long long c = c_lo; c <= c_hi; ++c) {
+        if (unit_begin(c, p.U, G) == unit_begin(c + 1, p.U, G)) continue;
         const long long slot = 2 * c + ((unit_begin(c, p.U, G) >= ub) ? 0 : 1);
         s += p.partG[((size_t)slot * TILE_B + row) * C::NP + j];
       }
@@ -292,6 +294,7 @@ thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_
   THY_TRY(m->ws.partL.reserve((size_t)2 * G * TILE_B));
   p.partG = m->ws.partG.ptr;
   p.partL = m->ws.partL.ptr;
+  KernelTimer timer(m, s);
   if (want_grad) {
     THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fused_dmma<NT, true><<<G, (NW + 1) * 32, smem, s>>>(p);
@@ -299,6 +302,7 @@ thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_
     THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fused_dmma<NT, false><<<G, (NW + 1) * 32, smem, s>>>(p);
   }
+  timer.stop();
   k_fused_finish<NT><<<(unsigned)ceil_div(p.B, 8), 256, 0, s>>>(p, G);
   count_launch(2);
   THY_CUDA_CHECK(cudaGetLastError());

@@ -99,6 +99,9 @@ struct thy_model_s {
   std::vector<std::unique_ptr<thy::LikDevOwner>> lik_dev;
   thy::Workspace ws;
   const char* last_path = "none";
+  // optional CUDA-event timing of the dominant kernel (bench.py's roofline leg)
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
   // host copies kept for prior sampling
   std::vector<int> h_kind;
   std::vector<double> h_p0, h_p1;
@@ -110,6 +113,22 @@ struct thy_model_s {
 };
 
 namespace thy {
+// Records a CUDA-event pair around the dominant kernel on the launching stream when timing is enabled.
+struct KernelTimer {
+  thy_model_s* m;
+  cudaStream_t s;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(thy_model_s* m_, cudaStream_t s_) : m(m_), s(s_) {
+    if (m->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, s);
+  }
+  void stop() {
+    if (e0 && e1) {
+      cudaEventRecord(e1, s);
+      m->timing_events.emplace_back(e0, e1);
+      e0 = e1 = nullptr;
+    }
+  }
+};
 // eval.cu
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false);
 // sampling.cu
