@@ -147,6 +147,41 @@ thy_status thy_sample_priors_dev(thy_model_t m, int64_t B, uint64_t rng_seed, do
 /* Name of the kernel path the last evaluation on this model used ("fused_dmma", "stream", "generic", ...). */
 const char* thy_model_last_kernel_path(thy_model_t m);
 
+/* ---- Hamiltonian MCMC ------------------------------------------------------------------------------
+ * HmcmcSampledPosterior.apply(hmcmcConfig, posterior, telemetryUpdateCallback, seed)
+ *   components/posterior/HmcmcSampledPosterior.scala:63-75; engine sampling/hmcmc/HmcmcEngine.scala:55-214;
+ *   config fields config/HmcmcConfig.scala:20-25 (same names).  n_chains independent chains run in lock-step. */
+typedef struct thy_hmcmc_config {
+  int stepsBetweenSamples;
+  int stepsInDynamicsSimulation;
+  int warmupStepCount;
+  double dynamicsSimulationStepSize;
+} thy_hmcmc_config;
+
+/* seed_points: host [n_chains * d] starting points (the reference's `seed`), or NULL => prior draws
+ * (HmcmcEngine.scala:183-188).  Samplers always use the mathematically correct Cauchy gradient sign.    */
+thy_status thy_hmc_create(thy_model_t m, const thy_hmcmc_config* cfg, int64_t n_chains, uint64_t rng_seed,
+                          const double* seed_points, thy_hmc_t* out);
+thy_status thy_hmc_destroy(thy_hmc_t h);
+/* Replay one trajectory from a CUDA graph (default on; needs a non-default stream set on the model). */
+thy_status thy_hmc_set_use_graph(thy_hmc_t h, int enable);
+/* burnIn (HmcmcEngine.scala:180-197): (re)initialise the chains and run warmupStepCount + 1 trajectories. */
+thy_status thy_hmc_burn_in(thy_hmc_t h);
+/* Run n_trajectories more trajectories on every chain (each = stepsInDynamicsSimulation leapfrog steps + one
+ * Metropolis test); asynchronous on the model's stream.  The benchmark's "leapfrog steps/s" loop.          */
+thy_status thy_hmc_run_trajectories(thy_hmc_t h, int n_trajectories);
+/* ModelParameterSampler.sample(n) (sampling/ModelParameterSampler.scala:36-37) for every chain:
+ * out_samples[(chain * n_per_chain + k) * d + j].  stepsBetweenSamples + 1 trajectories per block; a block in which
+ * a chain accepted nothing emits no sample for that chain (the reference's Set semantics, HmcmcEngine.scala:149-152).
+ * rerun_burn_in != 0 reproduces the reference (burn-in re-executes on every sample call, :205-207).          */
+thy_status thy_hmc_sample(thy_hmc_t h, int n_per_chain, double* out_samples, int rerun_burn_in);
+thy_status thy_hmc_sample_dev(thy_hmc_t h, int n_per_chain, double* out_samples_dev, int rerun_burn_in);
+/* HmcmcTelemetryUpdate fields (core/telemetry/HmcmcTelemetryUpdate.scala:20-25) per chain; any pointer may be NULL. */
+thy_status thy_hmc_stats(thy_hmc_t h, int64_t* out_jump_attempts, int64_t* out_jump_acceptances,
+                         double* out_hamiltonian_differential);
+/* Current positions [n_chains * d] and log-posteriors [n_chains] (checkpoint / warm start). */
+thy_status thy_hmc_get_state(thy_hmc_t h, double* out_x, double* out_logp);
+
 /* Measurement hook: when enabled, a CUDA-event pair is recorded on the model's stream around the dominant kernel of
  * every evaluation; thy_model_kernel_time synchronises, returns the summed duration and launch count, and resets. */
 thy_status thy_model_enable_timing(thy_model_t m, int enable);

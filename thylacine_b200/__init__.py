@@ -10,3 +10,4 @@ from .api import (  # noqa: F401
     CauchyLikelihood, CauchyPrior, GaussianLikelihood, GaussianLinearLikelihood, GaussianPrior, LinearForwardModel,
     NonLinearForwardModel, UniformLikelihood, UniformPrior, UnnormalisedPosterior, kernelLaunchCount,
 )
+from .samplers import HmcmcConfig, HmcmcSampledPosterior, HmcmcTelemetryUpdate  # noqa: F401,E402

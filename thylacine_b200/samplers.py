@@ -1,3 +1,133 @@
-"""Samplers and integrators built on the batched posterior (HMC, Leapfrog-MCMC, SLQ) -- bindings are
-registered here as the C-ABI entry points land."""
+"""Samplers and integrators built on the batched posterior -- host-side mirror of the reference's
+``HmcmcSampledPosterior`` / ``LeapfrogMcmcSampledPosterior`` / ``SlqIntegratedPosterior`` case classes.
+
+Paths relative to /root/reference/src/main/scala/thylacine/:
+    config/HmcmcConfig.scala:20-25, model/components/posterior/HmcmcSampledPosterior.scala:63-75,
+    model/sampling/hmcmc/HmcmcEngine.scala:55-214, model/sampling/ModelParameterSampler.scala:27-38
+"""
 from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import HmcmcConfigC, check, lib, register
+from .api import UnnormalisedPosterior, _arr, _ptr
+
+_vp, _dp = C.c_void_p, C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+register("thy_hmc_create", C.c_int, [_vp, C.POINTER(HmcmcConfigC), C.c_int64, C.c_uint64, _dp, C.POINTER(_vp)])
+register("thy_hmc_destroy", C.c_int, [_vp])
+register("thy_hmc_set_use_graph", C.c_int, [_vp, C.c_int])
+register("thy_hmc_burn_in", C.c_int, [_vp])
+register("thy_hmc_run_trajectories", C.c_int, [_vp, C.c_int])
+register("thy_hmc_sample", C.c_int, [_vp, C.c_int, _dp, C.c_int])
+register("thy_hmc_sample_dev", C.c_int, [_vp, C.c_int, _vp, C.c_int])
+register("thy_hmc_stats", C.c_int, [_vp, _i64p, _i64p, _dp])
+register("thy_hmc_get_state", C.c_int, [_vp, _dp, _dp])
+
+
+@dataclass
+class HmcmcConfig:
+    """config/HmcmcConfig.scala:20-25"""
+    stepsBetweenSamples: int
+    stepsInDynamicsSimulation: int
+    warmupStepCount: int
+    dynamicsSimulationStepSize: float
+
+
+@dataclass
+class HmcmcTelemetryUpdate:
+    """core/telemetry/HmcmcTelemetryUpdate.scala:20-25"""
+    samplesRemaining: int
+    jumpAttempts: int
+    jumpAcceptances: int
+    hamiltonianDifferential: Optional[float]
+
+
+class HmcmcSampledPosterior:
+    """``HmcmcSampledPosterior(hmcmcConfig, posterior, telemetryUpdateCallback, seed)``.
+
+    ``numberOfChains`` independent chains run in lock-step on the device (the reference runs one);
+    ``seed`` is the reference's starting point (a ``Map[String, Vector[Double]]``, shared by all chains,
+    or a (numberOfChains, d) array); omitted => prior draws (HmcmcEngine.scala:183-188).
+    ``sample(n)`` reproduces the reference: burn-in re-runs on every call (:205-207), stepsBetweenSamples+1
+    trajectories per sample (:168), fully rejected blocks add no sample (:149-152).
+    """
+
+    def __init__(self, hmcmcConfig: HmcmcConfig, posterior: UnnormalisedPosterior,
+                 telemetryUpdateCallback: Optional[Callable[[HmcmcTelemetryUpdate], None]] = None,
+                 seed=None, numberOfChains: int = 1, rngSeed: int = 0, useGraph: bool = True):
+        self.posterior = posterior
+        self.config = hmcmcConfig
+        self.numberOfChains = int(numberOfChains)
+        self.telemetryUpdateCallback = telemetryUpdateCallback
+        self._lib = lib()
+        cfg = HmcmcConfigC(hmcmcConfig.stepsBetweenSamples, hmcmcConfig.stepsInDynamicsSimulation,
+                           hmcmcConfig.warmupStepCount, float(hmcmcConfig.dynamicsSimulationStepSize))
+        seed_arr = None
+        if seed is not None:
+            if isinstance(seed, Mapping):
+                flat = posterior.flatten(seed)
+                seed_arr = np.ascontiguousarray(np.tile(flat[None, :], (self.numberOfChains, 1)))
+            else:
+                seed_arr = _arr(seed).reshape(self.numberOfChains, posterior.domainDimension)
+        h = C.c_void_p()
+        check(self._lib.thy_hmc_create(posterior.handle, C.byref(cfg), self.numberOfChains, rngSeed,
+                                       _ptr(seed_arr) if seed_arr is not None else None, C.byref(h)))
+        self._h = h
+        if not useGraph:
+            check(self._lib.thy_hmc_set_use_graph(h, 0))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.thy_hmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- reference surface
+    def sample(self, numberOfSamples: int) -> List[Dict[str, np.ndarray]]:
+        """Samples of chain 0 as labelled collections (the reference returns a Set of these)."""
+        chains = self.sampleChains(numberOfSamples)
+        return [self.posterior.unflatten(x) for x in chains[0]]
+
+    # -- batched surface
+    def sampleChains(self, numberOfSamples: int, rerunBurnIn: bool = True) -> np.ndarray:
+        out = np.empty((self.numberOfChains, numberOfSamples, self.posterior.domainDimension))
+        check(self._lib.thy_hmc_sample(self._h, numberOfSamples, _ptr(out), 1 if rerunBurnIn else 0))
+        if self.telemetryUpdateCallback is not None:
+            att, acc, dh = self.stats()
+            self.telemetryUpdateCallback(HmcmcTelemetryUpdate(0, int(att[0]), int(acc[0]), float(dh[0])))
+        return out
+
+    def burnIn(self) -> None:
+        check(self._lib.thy_hmc_burn_in(self._h))
+
+    def runTrajectories(self, n: int) -> None:
+        check(self._lib.thy_hmc_run_trajectories(self._h, n))
+
+    def stats(self):
+        att = np.empty(self.numberOfChains, dtype=np.int64)
+        acc = np.empty(self.numberOfChains, dtype=np.int64)
+        dh = np.empty(self.numberOfChains)
+        check(self._lib.thy_hmc_stats(self._h, att.ctypes.data_as(_i64p), acc.ctypes.data_as(_i64p), _ptr(dh)))
+        return att, acc, dh
+
+    def state(self):
+        x = np.empty((self.numberOfChains, self.posterior.domainDimension))
+        lp = np.empty(self.numberOfChains)
+        check(self._lib.thy_hmc_get_state(self._h, _ptr(x), _ptr(lp)))
+        return x, lp
