@@ -182,6 +182,33 @@ thy_status thy_hmc_stats(thy_hmc_t h, int64_t* out_jump_attempts, int64_t* out_j
 /* Current positions [n_chains * d] and log-posteriors [n_chains] (checkpoint / warm start). */
 thy_status thy_hmc_get_state(thy_hmc_t h, double* out_x, double* out_logp);
 
+/* ---- Leapfrog MCMC (gradient-free ensemble sampler) -----------------------------------------------
+ * LeapfrogMcmcSampledPosterior.of(leapfrogMcmcConfig, distanceCalculation, posterior, setCb, updateCb, seed)
+ *   components/posterior/LeapfrogMcmcSampledPosterior.scala:72-106; engine sampling/leapfrog/LeapfrogMcmcEngine.scala:88-294;
+ *   config fields config/LeapfrogMcmcConfig.scala:20-24.  The reference's distanceCalculation is a JVM closure
+ *   (LeapfrogMcmcSampledPosterior.scala:39); the device registry offers the named distances below.            */
+typedef struct thy_leapfrog_mcmc_config {
+  int stepsBetweenSamples;
+  int warmupStepCount;
+  int samplePoolSize;
+} thy_leapfrog_mcmc_config;
+typedef enum thy_distance {
+  THY_DISTANCE_EUCLIDEAN = 0, THY_DISTANCE_SQUARED_EUCLIDEAN = 1, THY_DISTANCE_MANHATTAN = 2
+} thy_distance;
+
+/* Draws the pool from the priors (slot 0 <- seed_point if given, LeapfrogMcmcEngine.scala:237-253), evaluates the
+ * pool's logPdfs and runs the burn-in (warmupStepCount proposals per pool member) before returning, as `.of` does. */
+thy_status thy_lfm_create(thy_model_t m, const thy_leapfrog_mcmc_config* cfg, int distance, uint64_t rng_seed,
+                          const double* seed_point, thy_lfm_t* out);
+thy_status thy_lfm_destroy(thy_lfm_t h);
+/* One sweep = one proposal for every pool member (two half-pool passes); asynchronous on the model's stream. */
+thy_status thy_lfm_run_sweeps(thy_lfm_t h, int n_sweeps);
+/* sample(n): each returned point has been proposed stepsBetweenSamples times since it was last handed out
+ * (LeapfrogMcmcEngine.scala:164-170,196-208).  out_samples: host [n * d].                                  */
+thy_status thy_lfm_sample(thy_lfm_t h, int n, double* out_samples);
+thy_status thy_lfm_stats(thy_lfm_t h, uint64_t* out_proposals, uint64_t* out_acceptances);
+thy_status thy_lfm_get_pool(thy_lfm_t h, double* out_x, double* out_logp);
+
 /* Measurement hook: when enabled, a CUDA-event pair is recorded on the model's stream around the dominant kernel of
  * every evaluation; thy_model_kernel_time synchronises, returns the summed duration and launch count, and resets. */
 thy_status thy_model_enable_timing(thy_model_t m, int enable);

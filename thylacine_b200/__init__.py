@@ -11,3 +11,4 @@ from .api import (  # noqa: F401
     NonLinearForwardModel, UniformLikelihood, UniformPrior, UnnormalisedPosterior, kernelLaunchCount,
 )
 from .samplers import HmcmcConfig, HmcmcSampledPosterior, HmcmcTelemetryUpdate  # noqa: F401,E402
+from .samplers import LeapfrogMcmcConfig, LeapfrogMcmcSampledPosterior  # noqa: F401,E402

@@ -29,6 +29,16 @@ register("thy_hmc_sample", C.c_int, [_vp, C.c_int, _dp, C.c_int])
 register("thy_hmc_sample_dev", C.c_int, [_vp, C.c_int, _vp, C.c_int])
 register("thy_hmc_stats", C.c_int, [_vp, _i64p, _i64p, _dp])
 register("thy_hmc_get_state", C.c_int, [_vp, _dp, _dp])
+register("thy_lfm_create", C.c_int, [_vp, C.c_void_p, C.c_int, C.c_uint64, _dp, C.POINTER(_vp)])
+register("thy_lfm_destroy", C.c_int, [_vp])
+register("thy_lfm_run_sweeps", C.c_int, [_vp, C.c_int])
+register("thy_lfm_sample", C.c_int, [_vp, C.c_int, _dp])
+register("thy_lfm_stats", C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+register("thy_lfm_get_pool", C.c_int, [_vp, _dp, _dp])
+
+
+class _LeapfrogMcmcConfigC(C.Structure):
+    _fields_ = [("stepsBetweenSamples", C.c_int), ("warmupStepCount", C.c_int), ("samplePoolSize", C.c_int)]
 
 
 @dataclass
@@ -130,4 +140,83 @@ class HmcmcSampledPosterior:
         x = np.empty((self.numberOfChains, self.posterior.domainDimension))
         lp = np.empty(self.numberOfChains)
         check(self._lib.thy_hmc_get_state(self._h, _ptr(x), _ptr(lp)))
+        return x, lp
+
+
+@dataclass
+class LeapfrogMcmcConfig:
+    """config/LeapfrogMcmcConfig.scala:20-24"""
+    stepsBetweenSamples: int
+    warmupStepCount: int
+    samplePoolSize: int
+
+
+DISTANCES = {"euclidean": 0, "squared_euclidean": 1, "manhattan": 2}
+
+
+class LeapfrogMcmcSampledPosterior:
+    """``LeapfrogMcmcSampledPosterior.of(leapfrogMcmcConfig, distanceCalculation, posterior, ..., seed)``
+    (components/posterior/LeapfrogMcmcSampledPosterior.scala:72-106).  ``distanceCalculation`` must name a device
+    distance ("euclidean", "squared_euclidean", "manhattan"): a JVM/Python closure cannot run on the GPU."""
+
+    def __init__(self, *a, **k):
+        raise TypeError("use LeapfrogMcmcSampledPosterior.of(...), as in the reference")
+
+    @classmethod
+    def of(cls, leapfrogMcmcConfig: LeapfrogMcmcConfig, distanceCalculation, posterior: UnnormalisedPosterior,
+           sampleRequestSetCallback=None, sampleRequestUpdateCallback=None, seed=None, rngSeed: int = 0):
+        if callable(distanceCalculation):
+            raise TypeError("distanceCalculation must be the name of a device-registered distance; closures cannot run on the GPU")
+        self = object.__new__(cls)
+        self.posterior = posterior
+        self.config = leapfrogMcmcConfig
+        self._lib = lib()
+        self._set_cb, self._update_cb = sampleRequestSetCallback, sampleRequestUpdateCallback
+        cfg = _LeapfrogMcmcConfigC(leapfrogMcmcConfig.stepsBetweenSamples, leapfrogMcmcConfig.warmupStepCount,
+                                   leapfrogMcmcConfig.samplePoolSize)
+        seed_arr = None
+        if seed is not None:
+            seed_arr = posterior.flatten(seed) if isinstance(seed, Mapping) else _arr(seed).reshape(posterior.domainDimension)
+        h = C.c_void_p()
+        check(self._lib.thy_lfm_create(posterior.handle, C.byref(cfg), DISTANCES[distanceCalculation], rngSeed,
+                                       _ptr(seed_arr) if seed_arr is not None else None, C.byref(h)))
+        self._h = h
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.thy_lfm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sample(self, numberOfSamples: int) -> List[Dict[str, np.ndarray]]:
+        return [self.posterior.unflatten(x) for x in self.sampleArray(numberOfSamples)]
+
+    def sampleArray(self, numberOfSamples: int) -> np.ndarray:
+        if self._set_cb is not None:
+            self._set_cb(numberOfSamples)
+        out = np.empty((numberOfSamples, self.posterior.domainDimension))
+        check(self._lib.thy_lfm_sample(self._h, numberOfSamples, _ptr(out)))
+        if self._update_cb is not None:
+            self._update_cb(0)
+        return out
+
+    def runSweeps(self, n: int) -> None:
+        check(self._lib.thy_lfm_run_sweeps(self._h, n))
+
+    def stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self._lib.thy_lfm_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def pool(self):
+        P = self.config.samplePoolSize
+        x = np.empty((P, self.posterior.domainDimension))
+        lp = np.empty(P)
+        check(self._lib.thy_lfm_get_pool(self._h, _ptr(x), _ptr(lp)))
         return x, lp
