@@ -209,6 +209,74 @@ thy_status thy_lfm_sample(thy_lfm_t h, int n, double* out_samples);
 thy_status thy_lfm_stats(thy_lfm_t h, uint64_t* out_proposals, uint64_t* out_acceptances);
 thy_status thy_lfm_get_pool(thy_lfm_t h, double* out_x, double* out_logp);
 
+/* ---- multi-GPU plumbing ---------------------------------------------------------------------------
+ * The reference has no distributed layer (single JVM process).  Here: one process per GPU; chains, pool members and
+ * live points shard across ranks; NCCL over NVLink is used only for the SLQ global lowest-logL selection and for
+ * sample-moment sums.  The 128-byte unique id is created on rank 0 and handed to the other ranks out of band
+ * (torch.distributed object broadcast, a file, the JVM's own RPC ...).  world == 1 needs no NCCL at all.      */
+typedef struct thy_comm_s* thy_comm_t;
+thy_status thy_comm_unique_id(unsigned char out_id[128]);
+thy_status thy_comm_create(int rank, int world, const unsigned char unique_id[128], thy_comm_t* out);
+thy_status thy_comm_destroy(thy_comm_t c);
+thy_status thy_comm_rank(thy_comm_t c, int* out_rank, int* out_world);
+/* In-place sum of a device fp64 buffer over all ranks on the given stream (no-op for world == 1 / NULL comm). */
+thy_status thy_comm_all_reduce_sum(thy_comm_t c, double* buf_dev, int64_t count, void* cuda_stream);
+
+/* ---- sample moments ---------------------------------------------------------------------------------
+ * Not in the reference (its tests compare sample means by hand, GaussianAnalyticPosteriorSpec.scala:34-50); required
+ * for the statistical parity checks.  acc_dev holds [count, sum x (d), sum x x^T (d*d)] = 1 + d + d*d doubles.   */
+thy_status thy_moments_reset_dev(thy_model_t m, double* acc_dev);
+/* acc += moments of X_dev[n][d]; rows whose first coordinate is NaN are skipped (unfilled HMC sample slots). */
+thy_status thy_moments_accumulate_dev(thy_model_t m, int64_t n, const double* X_dev, double* acc_dev);
+/* All-reduce over comm (may be NULL), then count, mean[d] and covariance[d*d] (unbiased) to host buffers. */
+thy_status thy_moments_finish(thy_model_t m, thy_comm_t comm, double* acc_dev, double* out_count, double* out_mean,
+                              double* out_cov);
+
+/* ---- SLQ (stochastic Lebesgue quadrature; nested sampling) ------------------------------------------
+ * SlqIntegratedPosterior.of(slqConfig, posterior, callbacks, seedsSpec)
+ *   components/posterior/SlqIntegratedPosterior.scala:87-125; engine integration/slq/SlqEngine.scala:107-469;
+ *   config fields config/SlqConfig.scala:20-28 (same names).  Live points shard across the ranks of `comm`.   */
+typedef struct thy_slq_config {
+  int poolSize;                       /* live points (global)                                                  */
+  int abscissaNumber;                 /* independent prior-mass simulations (QuadratureAbscissa.scala:33-73)   */
+  double domainScalingIncrement;      /* multiplicative step of the proposal-scale controller                  */
+  double targetAcceptanceProbability;
+  int sampleParallelism;              /* live points retired and replaced per round (reference: fibres in flight) */
+  int maxIterationCount;
+  int minIterationCount;
+  /* extensions (0 => default) */
+  int constrainedWalkSteps;           /* constrained-walk steps per replacement (default 20)                   */
+  int keepRetiredPoints;              /* keep retired positions for thy_slq_sample (single GPU)                */
+} thy_slq_config;
+
+typedef struct thy_slq_stats {
+  int64_t iterations;                 /* points retired during the live phase (SlqTelemetryUpdate.iterationCount) */
+  int64_t total_retired;              /* + the drained pool (SlqEngine.scala:171-180)                          */
+  int64_t rounds;
+  int64_t likelihood_evaluations;
+  double log_evidence_mean;           /* mean over abscissas of ln Z                                           */
+  double log_evidence_std;            /* spread over abscissas                                                 */
+  double neg_entropy_mean;            /* SlqTelemetryUpdate.negEntropyAvg                                      */
+  double min_logpdf;                  /* SlqTelemetryUpdate.samplePoolMinimumLogPdf at the end of the live phase */
+  double walk_scale;                  /* SlqTelemetryUpdate.domainVolumeScaling analogue                       */
+  double walk_acceptance;
+} thy_slq_stats;
+
+/* seeds: host [n_seeds * d] points placed in the first pool slots of rank 0 (SlqEngine.scala:384-389,409), or NULL. */
+thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng_seed, const double* seeds, int n_seeds,
+                          thy_comm_t comm, thy_slq_t* out);
+thy_status thy_slq_destroy(thy_slq_t h);
+/* rebuildSampleSimulation (SlqIntegratedPosterior.scala:76-80): run to convergence / maxIterationCount, drain. */
+thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats);
+/* Run at most n_rounds more rounds of the live phase without draining (the benchmark's loop); *out_converged set. */
+thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged);
+/* Retired log-likelihoods in retirement order; *out_count receives the total available. */
+thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, int64_t* out_count);
+/* Per-abscissa ln Z_a and H_a of the quadrature so far (QuadratureIntegrator.scala:29-62); [abscissaNumber] each. */
+thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, double* out_neg_entropy);
+/* sample(n) (SamplingSimulation.scala:41-101): posterior resampling of retired points; needs keepRetiredPoints. */
+thy_status thy_slq_sample(thy_slq_t h, int n, uint64_t rng_seed, double* out_samples);
+
 /* Measurement hook: when enabled, a CUDA-event pair is recorded on the model's stream around the dominant kernel of
  * every evaluation; thy_model_kernel_time synchronises, returns the summed duration and launch count, and resets. */
 thy_status thy_model_enable_timing(thy_model_t m, int enable);

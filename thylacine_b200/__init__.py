@@ -12,3 +12,5 @@ from .api import (  # noqa: F401
 )
 from .samplers import HmcmcConfig, HmcmcSampledPosterior, HmcmcTelemetryUpdate  # noqa: F401,E402
 from .samplers import LeapfrogMcmcConfig, LeapfrogMcmcSampledPosterior  # noqa: F401,E402
+from .samplers import SampleMoments, SlqConfig, SlqIntegratedPosterior, SlqTelemetryUpdate  # noqa: F401,E402
+from .distributed import Communicator, shard_range  # noqa: F401,E402

@@ -1,0 +1,137 @@
+// NCCL over NVLink 5 / NVSwitch, used only where the path has a real exchange step (DESIGN.md "Multi-GPU"):
+// the SLQ global lowest-logL selection (all-gather of each rank's K smallest) and sample-moment sums (all-reduce).
+// The reference has no collectives at all (single JVM process).
+#include "comm.h"
+#include <dlfcn.h>
+#include <cstring>
+
+namespace thy {
+
+namespace {
+typedef int ncclResult_t;
+struct ncclUniqueId { char internal[128]; };
+typedef void* ncclComm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclInt64 = 4, kNcclFloat64 = 8;
+
+NcclApi& api() {
+  static NcclApi a;
+  if (a.lib) return a;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) return a;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+  a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.GetErrorString;
+  return a;
+}
+
+thy_status nccl_fail(ncclResult_t r, const char* what) {
+  return fail(THY_ERR_NCCL, std::string(what) + ": " + (api().GetErrorString ? api().GetErrorString(r) : "nccl error"));
+}
+}  // namespace
+
+thy_status comm_all_gather_f64(thy_comm_s* c, const double* send, double* recv, size_t count, cudaStream_t s) {
+  if (!c || c->world == 1) {
+    if (send != recv) THY_CUDA_CHECK(cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return THY_OK;
+  }
+  ncclResult_t r = api().AllGather(send, recv, count, kNcclFloat64, c->nccl_comm, s);
+  return r == 0 ? THY_OK : nccl_fail(r, "ncclAllGather");
+}
+
+thy_status comm_all_reduce_f64(thy_comm_s* c, double* buf, size_t count, int op, cudaStream_t s) {
+  if (!c || c->world == 1) return THY_OK;
+  ncclResult_t r = api().AllReduce(buf, buf, count, kNcclFloat64, op, c->nccl_comm, s);
+  return r == 0 ? THY_OK : nccl_fail(r, "ncclAllReduce");
+}
+
+thy_status comm_all_reduce_i64(thy_comm_s* c, long long* buf, size_t count, int op, cudaStream_t s) {
+  if (!c || c->world == 1) return THY_OK;
+  ncclResult_t r = api().AllReduce(buf, buf, count, kNcclInt64, op, c->nccl_comm, s);
+  return r == 0 ? THY_OK : nccl_fail(r, "ncclAllReduce");
+}
+
+}  // namespace thy
+
+using namespace thy;
+
+extern "C" {
+
+thy_status thy_comm_unique_id(unsigned char out_id[128]) {
+  if (!out_id) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  if (!api().ok) return fail(THY_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  ncclResult_t r = api().GetUniqueId(&id);
+  if (r != 0) return nccl_fail(r, "ncclGetUniqueId");
+  std::memcpy(out_id, id.internal, 128);
+  return THY_OK;
+}
+
+thy_status thy_comm_create(int rank, int world, const unsigned char unique_id[128], thy_comm_t* out) {
+  if (!out) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  if (world < 1 || rank < 0 || rank >= world) return fail(THY_ERR_INVALID_ARGUMENT, "bad rank / world");
+  auto* c = new (std::nothrow) thy_comm_s();
+  if (!c) return fail(THY_ERR_INVALID_ARGUMENT, "allocation failed");
+  c->rank = rank;
+  c->world = world;
+  if (world > 1) {
+    THY_TRY(require_device());
+    if (!unique_id) {
+      delete c;
+      return fail(THY_ERR_INVALID_ARGUMENT, "unique id required for world > 1");
+    }
+    if (!api().ok) {
+      delete c;
+      return fail(THY_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    }
+    ncclUniqueId id;
+    std::memcpy(id.internal, unique_id, 128);
+    ncclComm_t nc = nullptr;
+    ncclResult_t r = api().CommInitRank(&nc, world, id, rank);
+    if (r != 0) {
+      delete c;
+      return nccl_fail(r, "ncclCommInitRank");
+    }
+    c->nccl_comm = nc;
+  }
+  *out = c;
+  return THY_OK;
+}
+
+thy_status thy_comm_destroy(thy_comm_t c) {
+  if (c && c->nccl_comm && api().ok) api().CommDestroy((ncclComm_t)c->nccl_comm);
+  delete c;
+  return THY_OK;
+}
+
+thy_status thy_comm_rank(thy_comm_t c, int* out_rank, int* out_world) {
+  if (!c) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (out_rank) *out_rank = c->rank;
+  if (out_world) *out_world = c->world;
+  return THY_OK;
+}
+
+/* Sum of a device fp64 buffer over all ranks (sample moments: count, sum x, sum x x^T). */
+thy_status thy_comm_all_reduce_sum(thy_comm_t c, double* buf_dev, int64_t count, void* cuda_stream) {
+  THY_TRY(comm_all_reduce_f64(c, buf_dev, (size_t)count, 0, (cudaStream_t)cuda_stream));
+  return THY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,686 @@
+// SLQ (stochastic Lebesgue quadrature = nested sampling) with the live-point threshold step on the device.
+// Reference: /root/reference/src/main/scala/thylacine/model/integration/slq/
+//   SlqEngine.scala:120-197        live pool keyed by logPdf; discard the global minimum; replace it by a new draw
+//                                  accepted only above the threshold; per-acceptance abscissa extension
+//   SlqEngine.scala:249-277        convergence: iterations > minIterationCount && iterations >= 10 P H, or >= maxIterationCount
+//   SlqEngine.scala:171-180        drainSamplePool: remaining live points appended in ascending order
+//   QuadratureAbscissa.scala:33-73 prior-mass simulation: pool of P uniforms, max moved to the abscissa list (first = 1.0),
+//                                  trapezoid weights 1/2 (X_{i-1} - X_{i+1}), ends half the adjacent gap
+//   QuadratureIntegrator.scala:29-62  Z_a = sum w_i exp(l_i - s), H_a = sum w_i e^{l_i - s}(l_i - s)/Z_a - ln Z_a
+// Re-design for 10^6 live points (DESIGN.md "SLQ"): the K lowest live points are retired per round (K = sampleParallelism,
+// the reference's number of concurrent sampling fibres); thresholds come from a device radix sort plus, across GPUs, an
+// NCCL all-gather of each rank's K smallest; replacements are constrained random walks started from surviving live
+// points (the reference's O(P^2 d) cubical cover cannot exist at this size); prior-mass shrinkage is sampled directly as
+// t = u^{1/n_live} per abscissa in log space and the evidence is a streaming log-sum-exp (no BigDecimal needed).
+// Measure / integrand: points are drawn from the PRIOR and ranked by log-LIKELIHOOD, so ln Z is the calibrated
+// evidence (for uniform priors this coincides with the reference's uniform-domain / full-density formulation, Q6).
+#include "kernels.h"
+#include "comm.h"
+#include "philox.cuh"
+#include <cub/cub.cuh>
+#include <cmath>
+#include <algorithm>
+
+struct thy_slq_s {
+  thy_model_s* model = nullptr;
+  thy_comm_s* comm = nullptr;
+  thy_slq_config cfg{};
+  uint64_t seed = 0;
+  int world = 1, rank = 0;
+  long long P = 0, Pl = 0;   // global / local live points
+  int d = 0, A = 1, K = 1, M = 20;
+  thy::DevBuf<double> x, ll, lpr;                        // live pool
+  thy::DevBuf<double> keys_in, keys_out;                 // sort scratch
+  thy::DevBuf<int> idx_in, idx_out;
+  thy::DevBuf<unsigned char> cub_tmp;
+  thy::DevBuf<double> cand_all, cand_sorted;             // gathered candidates
+  thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers
+  thy::DevBuf<int> slot;
+  thy::DevBuf<double> sigma, sig_part;                   // per-dimension spread of the live pool
+  thy::DevBuf<double> scalars;                           // [0] walk scale, [1] threshold, [2] accepted, [3] proposed
+  thy::DevBuf<int> count_dev;                            // [0] local retire count
+  thy::DevBuf<double> tmp_logx;                          // [A][Kmax]
+  thy::DevBuf<double> abs_state;                         // [A][8]: logX_cur, Xm2, Xm1, pend_l, has_pend(0/1/2), m, s, s_l
+  thy::DevBuf<double> abs_out;                           // [A][2]: logZ, H
+  thy::DevBuf<double> ret_ll;                            // retired log-likelihoods (global order)
+  thy::DevBuf<double> ret_x;                             // retired points (optional, world == 1)
+  thy::DevBuf<double> ret_logw;                          // log posterior weight under the expected abscissa
+  long long iterations = 0, rounds = 0, evals = 0;
+  long long ret_capacity = 0;
+  bool finished = false;
+  thy_slq_stats stats{};
+};
+
+namespace thy {
+
+__global__ void k_iota(int n, int* v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+__global__ void k_sub(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+
+__global__ void k_fill(long long n, double* v, double val) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = val;
+}
+
+// threshold = merged[Kr-1]; local retire count = #sorted local keys <= threshold
+__global__ void k_slq_threshold(const double* __restrict__ merged, int Kr, const double* __restrict__ local_sorted,
+                                long long Pl, double* __restrict__ scalars, int* __restrict__ count) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double thr = merged[Kr - 1];
+  scalars[1] = thr;
+  long long lo = 0, hi = Pl;  // first index with key > thr
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (local_sorted[mid] <= thr) lo = mid + 1; else hi = mid;
+  }
+  count[0] = (int)lo;
+}
+
+// Per-dimension standard deviation of the live pool: deterministic two-stage reduction.
+__global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, int d, const double* __restrict__ x,
+                                                        double* __restrict__ part, int nslab) {
+  // block = one slab of rows; threads stride over columns (coalesced), rows sequential
+  const int slab = blockIdx.x;
+  const long long r0 = (Pl * slab) / nslab, r1 = (Pl * (slab + 1)) / nslab;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    double s = 0.0, s2 = 0.0;
+    for (long long r = r0; r < r1; ++r) {
+      const double v = x[r * d + j];
+      s += v;
+      s2 = fma(v, v, s2);
+    }
+    part[((size_t)slab * 2 + 0) * d + j] = s;
+    part[((size_t)slab * 2 + 1) * d + j] = s2;
+  }
+}
+__global__ void k_slq_sigma_final(long long Pl, int d, const double* __restrict__ part, int nslab, double* __restrict__ sigma) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  double s = 0.0, s2 = 0.0;
+  for (int b = 0; b < nslab; ++b) {
+    s += part[((size_t)b * 2 + 0) * d + j];
+    s2 += part[((size_t)b * 2 + 1) * d + j];
+  }
+  const double mean = s / Pl;
+  const double var = fmax(s2 / Pl - mean * mean, 0.0);
+  sigma[j] = sqrt(var);
+}
+
+// Walkers start from uniformly chosen survivors.
+__global__ void __launch_bounds__(256) k_slq_spawn(int c, long long Pl, int d, uint64_t seed, uint64_t round, int rank,
+                                                   const int* __restrict__ sidx, const double* __restrict__ x,
+                                                   const double* __restrict__ ll, const double* __restrict__ lpr,
+                                                   double* __restrict__ Y, double* __restrict__ yl, double* __restrict__ ypr,
+                                                   int* __restrict__ slot) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= c) return;
+  const RngDraw u = rng_uniform2(seed, ((uint64_t)rank << 40) | (uint64_t)w, 0, RNG_SLQ_PICK, round);
+  long long pick = c + (long long)(u.u0 * (double)(Pl - c));
+  if (pick >= Pl) pick = Pl - 1;
+  const int src = sidx[pick];
+  for (int j = lane; j < d; j += 32) Y[(size_t)w * d + j] = x[(size_t)src * d + j];
+  if (lane == 0) {
+    yl[w] = ll[src];
+    ypr[w] = lpr[src];
+    slot[w] = sidx[w];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_slq_propose(int c, int d, uint64_t seed, uint64_t step, int rank,
+                                                     const double* __restrict__ Y, const double* __restrict__ sigma,
+                                                     const double* __restrict__ scalars, double* __restrict__ Yp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)c * d) return;
+  const int w = (int)(i / d), j = (int)(i % d);
+  const double z = rng_normal(seed, ((uint64_t)rank << 40) | (uint64_t)w, (uint32_t)j, RNG_SLQ_MOVE, step);
+  Yp[i] = Y[i] + scalars[0] * sigma[j] * z;
+}
+
+// Metropolis test w.r.t. the prior, hard likelihood constraint L' > L*.
+__global__ void __launch_bounds__(256) k_slq_accept(int c, int d, uint64_t seed, uint64_t step, int rank,
+                                                    double* __restrict__ Y, double* __restrict__ yl, double* __restrict__ ypr,
+                                                    const double* __restrict__ Yp, const double* __restrict__ tl,
+                                                    const double* __restrict__ tpr, double* __restrict__ scalars) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= c) return;
+  const double lprior_new = tpr[w];
+  const double lnew = tl[w] - lprior_new;
+  const RngDraw u = rng_uniform2(seed, ((uint64_t)rank << 40) | (uint64_t)w, 0, RNG_SLQ_ACCEPT, step);
+  const bool ok = isfinite(lprior_new) && isfinite(lnew) && (lnew > scalars[1]) &&
+                  (lprior_new - ypr[w] >= log(1.0 - u.u0));
+  if (ok) {
+    for (int j = lane; j < d; j += 32) Y[(size_t)w * d + j] = Yp[(size_t)w * d + j];
+  }
+  if (lane == 0) {
+    if (ok) {
+      yl[w] = lnew;
+      ypr[w] = lprior_new;
+      atomicAdd(&scalars[2], 1.0);   // integer-valued counts: exact and order-independent in fp64
+    }
+    atomicAdd(&scalars[3], 1.0);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_slq_commit(int c, int d, const int* __restrict__ slot, const double* __restrict__ Y,
+                                                    const double* __restrict__ yl, const double* __restrict__ ypr,
+                                                    double* __restrict__ x, double* __restrict__ ll, double* __restrict__ lpr) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= c) return;
+  const int s = slot[w];
+  for (int j = lane; j < d; j += 32) x[(size_t)s * d + j] = Y[(size_t)w * d + j];
+  if (lane == 0) {
+    ll[s] = yl[w];
+    lpr[s] = ypr[w];
+  }
+}
+
+// scale *= (1 + inc) when the round's acceptance beat the target, else /= (1 + inc)   (SlqConfig.domainScalingIncrement,
+// targetAcceptanceProbability play the same role for the reference's cube scaling, QuadratureDomainTelemetry.scala)
+__global__ void k_slq_adapt(double* scalars, double inc, double target) {
+  if (scalars[3] > 0.0) {
+    const double rate = scalars[2] / scalars[3];
+    scalars[4] = rate;
+    if (rate > target) scalars[0] *= (1.0 + inc); else scalars[0] /= (1.0 + inc);
+    scalars[0] = fmin(fmax(scalars[0], 1e-6), 10.0);
+  }
+  scalars[5] += scalars[2];
+  scalars[6] += scalars[3];
+  scalars[2] = 0.0;
+  scalars[3] = 0.0;
+}
+
+// Copy retired points (local sorted order == global order when world == 1).
+__global__ void __launch_bounds__(256) k_slq_store(int c, int d, const int* __restrict__ sidx, const double* __restrict__ x,
+                                                   double* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= c) return;
+  const int s = sidx[w];
+  for (int j = lane; j < d; j += 32) dst[(size_t)w * d + j] = x[(size_t)s * d + j];
+}
+
+// ---- evidence accumulation -------------------------------------------------------------------------------------
+// One block per abscissa.  r[0..Kr) = retired log-likelihoods of this round in ascending order; the j-th of them was
+// retired with n0 - j points alive, so the prior mass shrinks by t = u^{1/(n0-j)} AFTER it has been assigned its X
+// (the reference assigns X = 1.0 to the very first retired point, QuadratureAbscissa.scala:64-73).
+// state: [0] logX assigned to the next point, [1] logX_{i-2}, [2] logX_{i-1}, [3] l_{i-1}, [4] pending count (0,1,2+),
+//        [5] running max m, [6] sum exp(term - m), [7] sum exp(term - m) * l
+__device__ __forceinline__ void lse_add(double& m, double& s, double& sl, double term, double l) {
+  if (!(term > -INFINITY)) return;
+  if (term > m) {
+    const double f = exp(m - term);
+    s = s * f + 1.0;
+    sl = sl * f + l;
+    m = term;
+  } else {
+    const double e = exp(term - m);
+    s += e;
+    sl += e * l;
+  }
+}
+__device__ __forceinline__ double log_half_gap(double lx_hi, double lx_lo) {
+  // ln( 1/2 (X_hi - X_lo) ),  X_hi >= X_lo given as logs
+  return log(0.5) + lx_hi + log(-expm1(lx_lo - lx_hi));
+}
+
+__global__ void __launch_bounds__(256) k_slq_evidence(int Kr, long long n0, long long it0, uint64_t seed,
+                                                      const double* __restrict__ r, double* __restrict__ tmp_logx,
+                                                      long long tmp_stride, double* __restrict__ state, int finalize,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[256];
+  __shared__ double carry;
+  __shared__ double red_m[256], red_s[256], red_sl[256];
+  const int a = blockIdx.x;
+  double* st = state + (size_t)a * 8;
+  double* lx = tmp_logx + (size_t)a * tmp_stride;
+  const int tid = threadIdx.x;
+  if (tid == 0) carry = st[0];
+  __syncthreads();
+  // pass 1: logX_j = logX_cur + sum_{k<j} ln t_k   (exclusive scan in chunks of 256)
+  for (int base = 0; base < Kr; base += 256) {
+    const int j = base + tid;
+    double lt = 0.0;
+    if (j < Kr) {
+      const RngDraw u = rng_uniform2(seed, (uint64_t)a, 0, RNG_SLQ_SHRINK, (uint64_t)(it0 + j));
+      lt = log(1.0 - u.u0) / (double)(n0 - j);   // ln u^{1/n}, u in (0,1]
+    }
+    sh[tid] = lt;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {  // inclusive Hillis-Steele scan
+      double v = (tid >= o) ? sh[tid - o] : 0.0;
+      __syncthreads();
+      sh[tid] += v;
+      __syncthreads();
+    }
+    const double incl = sh[tid];
+    const double c0 = carry;
+    if (j < Kr) lx[j] = c0 + incl - lt;
+    __syncthreads();
+    if (tid == 255) carry = c0 + incl;
+    __syncthreads();
+  }
+  // pass 2: finalise point j-1 once X_j is known: w_{j-1} = 1/2 (X_{j-2} - X_j)  (first ever point: 1/2 (X_0 - X_1))
+  double m = -INFINITY, s = 0.0, sl = 0.0;
+  const double pend = st[4];
+  for (int j = tid; j < Kr; j += 256) {
+    double l_prev, lx_m2;
+    bool have_prev = true, first_ever = false;
+    if (j == 0) {
+      if (pend < 0.5) have_prev = false;
+      l_prev = st[3];
+      lx_m2 = st[1];
+      first_ever = pend < 1.5;   // pending point is the very first retired point: no X_{i-2}
+      if (first_ever) lx_m2 = st[2];  // use X_{i-1} itself: 1/2 (X_0 - X_1)
+    } else if (j == 1) {
+      l_prev = r[0];
+      lx_m2 = st[2];
+      if (pend < 0.5) { first_ever = true; lx_m2 = lx[0]; }
+    } else {
+      l_prev = r[j - 1];
+      lx_m2 = lx[j - 2];
+    }
+    if (have_prev) {
+      const double term = l_prev + log_half_gap(lx_m2, lx[j]);
+      lse_add(m, s, sl, term, l_prev);
+    }
+  }
+  red_m[tid] = m; red_s[tid] = s; red_sl[tid] = sl;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      double m2 = red_m[tid + o], s2 = red_s[tid + o], sl2 = red_sl[tid + o];
+      double m1 = red_m[tid], s1 = red_s[tid], sl1 = red_sl[tid];
+      if (m2 > m1) { const double f = exp(m1 - m2); s1 = s1 * f + s2; sl1 = sl1 * f + sl2; m1 = m2; }
+      else if (m2 > -INFINITY) { const double f = exp(m2 - m1); s1 += s2 * f; sl1 += sl2 * f; }
+      red_m[tid] = m1; red_s[tid] = s1; red_sl[tid] = sl1;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double M = st[5], S = st[6], SL = st[7];
+    if (red_m[0] > -INFINITY) {
+      if (red_m[0] > M) { const double f = exp(M - red_m[0]); S = S * f + red_s[0]; SL = SL * f + red_sl[0]; M = red_m[0]; }
+      else { const double f = exp(red_m[0] - M); S += red_s[0] * f; SL += red_sl[0] * f; }
+    }
+    if (Kr > 0) {
+      // new pending point = last of this round
+      const double new_m1 = lx[Kr - 1];
+      const double new_m2 = (Kr >= 2) ? lx[Kr - 2] : st[2];
+      const double newpend = (Kr >= 2) ? 2.0 : (pend + 1.0);
+      st[1] = new_m2;
+      st[2] = new_m1;
+      st[3] = r[Kr - 1];
+      st[4] = newpend > 2.0 ? 2.0 : newpend;
+      st[0] = carry;
+    }
+    if (finalize && st[4] > 1.5) {
+      // last point: 1/2 (X_{N-2} - X_{N-1})
+      const double term = st[3] + log_half_gap(st[1], st[2]);
+      lse_add(M, S, SL, term, st[3]);
+      st[4] = 0.0;
+    }
+    st[5] = M; st[6] = S; st[7] = SL;
+    const double logZ = (S > 0.0) ? M + log(S) : -INFINITY;
+    out[a * 2 + 0] = logZ;
+    out[a * 2 + 1] = (S > 0.0) ? SL / S - logZ : 0.0;
+  }
+}
+
+static thy_status slq_sort_local(thy_slq_s* h) {
+  cudaStream_t s = h->model->stream;
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->keys_in.ptr, h->ll.ptr, h->Pl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->keys_in.ptr, h->keys_out.ptr, h->idx_in.ptr, h->idx_out.ptr, (int)h->Pl, 0, 64, s);
+  THY_TRY(h->cub_tmp.reserve(bytes));
+  THY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.ptr, bytes, h->keys_in.ptr, h->keys_out.ptr, h->idx_in.ptr,
+                                                 h->idx_out.ptr, (int)h->Pl, 0, 64, s));
+  count_launch(3);
+  return THY_OK;
+}
+
+static thy_status slq_sort_keys(thy_slq_s* h, const double* in, double* out, int n) {
+  cudaStream_t s = h->model->stream;
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, n, 0, 64, s);
+  THY_TRY(h->cub_tmp.reserve(bytes));
+  THY_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(h->cub_tmp.ptr, bytes, in, out, n, 0, 64, s));
+  count_launch(3);
+  return THY_OK;
+}
+
+// log-likelihood = total log-posterior - log-prior for a batch
+static thy_status slq_eval(thy_slq_s* h, long long n, const double* X, double* total, double* prior) {
+  thy_model_s* m = h->model;
+  THY_TRY(launch_prior(m->prior_view, n, X, prior, nullptr, -1.0, m->stream));
+  THY_TRY(eval_batch_dev(m, n, X, total, nullptr, true));
+  h->evals += n;
+  return THY_OK;
+}
+
+static thy_status slq_evidence(thy_slq_s* h, const double* retired_sorted, int Kr, long long n0, int finalize) {
+  cudaStream_t s = h->model->stream;
+  const long long stride = std::max<long long>(h->K, h->P);
+  k_slq_evidence<<<h->A, 256, 0, s>>>(Kr, n0, h->iterations, h->seed, retired_sorted, h->tmp_logx.ptr, stride,
+                                      h->abs_state.ptr, finalize, h->abs_out.ptr);
+  count_launch();
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
+}
+
+static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
+  thy_model_s* m = h->model;
+  cudaStream_t s = m->stream;
+  const int d = h->d;
+  THY_TRY(slq_sort_local(h));
+  // each rank contributes its Kr smallest; the Kr globally smallest are retired
+  const double* merged = h->keys_out.ptr;
+  if (h->world > 1) {
+    THY_TRY(comm_all_gather_f64(h->comm, h->keys_out.ptr, h->cand_all.ptr, (size_t)Kr, s));
+    THY_TRY(slq_sort_keys(h, h->cand_all.ptr, h->cand_sorted.ptr, Kr * h->world));
+    merged = h->cand_sorted.ptr;
+  }
+  k_slq_threshold<<<1, 32, 0, s>>>(merged, Kr, h->keys_out.ptr, h->Pl, h->scalars.ptr, h->count_dev.ptr);
+  count_launch();
+  int c = 0;
+  THY_CUDA_CHECK(cudaMemcpyAsync(&c, h->count_dev.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  // retired values recorded in global order (identical on every rank)
+  if (h->iterations + Kr > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, merged, (size_t)Kr * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, Kr, h->P, 0));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (c >= h->Pl) return fail(THY_ERR_STATE, "SLQ: a rank lost all of its live points in one round; lower sampleParallelism");
+  if (h->cfg.keepRetiredPoints && h->world == 1 && c > 0) {
+    k_slq_store<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->idx_out.ptr, h->x.ptr, h->ret_x.ptr + (size_t)h->iterations * d);
+    count_launch();
+  }
+  if (c > 0) {
+    // per-dimension spread of the live pool sets the walk's proposal shape
+    const int nslab = 128;
+    k_slq_sigma_part<<<nslab, 256, 0, s>>>(h->Pl, d, h->x.ptr, h->sig_part.ptr, nslab);
+    k_slq_sigma_final<<<(unsigned)ceil_div(d, 128), 128, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
+    k_slq_spawn<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, h->Pl, d, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr,
+                                                        h->x.ptr, h->ll.ptr, h->lpr.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
+                                                        h->slot.ptr);
+    count_launch(3);
+    for (int step = 0; step < h->M; ++step) {
+      const uint64_t gstep = (uint64_t)h->rounds * (uint64_t)h->M + step;
+      k_slq_propose<<<(unsigned)ceil_div((long long)c * d, 256), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr,
+                                                                               h->sigma.ptr, h->scalars.ptr, h->Yp.ptr);
+      THY_TRY(slq_eval(h, c, h->Yp.ptr, h->tl.ptr, h->tpr.ptr));
+      k_slq_accept<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
+                                                           h->Yp.ptr, h->tl.ptr, h->tpr.ptr, h->scalars.ptr);
+      count_launch(2);
+    }
+    k_slq_commit<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->slot.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr, h->x.ptr,
+                                                         h->ll.ptr, h->lpr.ptr);
+    k_slq_adapt<<<1, 1, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability);
+    count_launch(2);
+  }
+  THY_CUDA_CHECK(cudaGetLastError());
+  h->iterations += Kr;
+  h->rounds += 1;
+  if (out_local_count) *out_local_count = c;
+  return THY_OK;
+}
+
+}  // namespace thy
+
+using namespace thy;
+
+extern "C" {
+
+thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng_seed, const double* seeds, int n_seeds,
+                          thy_comm_t comm, thy_slq_t* out) {
+  THY_TRY(require_device());
+  if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
+  if (!cfg || !out) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  if (m->lik_dev.empty()) return fail(THY_ERR_INVALID_ARGUMENT, "SLQ needs at least one likelihood");
+  const int world = comm ? comm->world : 1;
+  if (cfg->poolSize < 4 * world) return fail(THY_ERR_INVALID_ARGUMENT, "poolSize too small");
+  if (cfg->poolSize % world != 0) return fail(THY_ERR_INVALID_ARGUMENT, "poolSize must be divisible by the number of ranks");
+  if (cfg->abscissaNumber < 1 || cfg->abscissaNumber > 1024) return fail(THY_ERR_INVALID_ARGUMENT, "abscissaNumber out of range");
+  if (cfg->maxIterationCount < 1 || cfg->minIterationCount < 0) return fail(THY_ERR_INVALID_ARGUMENT, "bad iteration counts");
+  if (!(cfg->domainScalingIncrement > 0) || !(cfg->targetAcceptanceProbability > 0 && cfg->targetAcceptanceProbability < 1))
+    return fail(THY_ERR_INVALID_ARGUMENT, "bad scaling increment / target acceptance");
+  if (n_seeds < 0 || (n_seeds > 0 && !seeds)) return fail(THY_ERR_INVALID_ARGUMENT, "bad seeds");
+  auto* h = new (std::nothrow) thy_slq_s();
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "allocation failed");
+  h->model = m;
+  h->comm = comm;
+  h->cfg = *cfg;
+  h->seed = rng_seed;
+  h->world = world;
+  h->rank = comm ? comm->rank : 0;
+  h->P = cfg->poolSize;
+  h->Pl = h->P / world;
+  h->d = m->d;
+  h->A = cfg->abscissaNumber;
+  h->M = cfg->constrainedWalkSteps > 0 ? cfg->constrainedWalkSteps : 20;
+  int K = cfg->sampleParallelism > 0 ? cfg->sampleParallelism : 1;
+  K = (int)std::min<long long>(K, std::max<long long>(1, h->Pl / 4));   // every rank must keep survivors
+  h->K = K;
+  h->ret_capacity = (long long)cfg->maxIterationCount + K + h->P;
+  const int d = h->d;
+  const long long Pl = h->Pl;
+  thy_status st = THY_OK;
+  auto chk = [&](thy_status s2) { if (st == THY_OK) st = s2; };
+  chk(h->x.reserve((size_t)Pl * d)); chk(h->ll.reserve(Pl)); chk(h->lpr.reserve(Pl));
+  chk(h->keys_in.reserve(Pl)); chk(h->keys_out.reserve(Pl)); chk(h->idx_in.reserve(Pl)); chk(h->idx_out.reserve(Pl));
+  chk(h->cand_all.reserve((size_t)std::max<long long>((long long)K * world, h->P)));
+  chk(h->cand_sorted.reserve((size_t)std::max<long long>((long long)K * world, h->P)));
+  chk(h->Y.reserve((size_t)K * d)); chk(h->Yp.reserve((size_t)K * d)); chk(h->yl.reserve(K)); chk(h->ypr.reserve(K));
+  chk(h->tl.reserve(K)); chk(h->tpr.reserve(K)); chk(h->slot.reserve(K));
+  chk(h->sigma.reserve(d)); chk(h->sig_part.reserve((size_t)128 * 2 * d));
+  chk(h->scalars.reserve(8)); chk(h->count_dev.reserve(1));
+  chk(h->tmp_logx.reserve((size_t)h->A * std::max<long long>(K, h->P)));
+  chk(h->abs_state.reserve((size_t)h->A * 8)); chk(h->abs_out.reserve((size_t)h->A * 2));
+  chk(h->ret_ll.reserve((size_t)h->ret_capacity));
+  if (cfg->keepRetiredPoints) {
+    if (world != 1) chk(fail(THY_ERR_UNSUPPORTED, "keepRetiredPoints is single-GPU only in this version"));
+    chk(h->ret_x.reserve((size_t)h->ret_capacity * d));
+  }
+  cudaStream_t s = m->stream;
+  if (st == THY_OK) {
+    // initial pool: prior draws (+ seeds in the first slots, SlqEngine.scala:384-389,409)
+    chk(sample_priors_dev(m, Pl, rng_seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(h->rank + 1)), h->x.ptr));
+    if (st == THY_OK && n_seeds > 0 && h->rank == 0) {
+      const long long ns = std::min<long long>(n_seeds, Pl);
+      if (cudaMemcpyAsync(h->x.ptr, seeds, (size_t)ns * d * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess)
+        st = fail(THY_ERR_CUDA, "seed upload failed");
+    }
+  }
+  if (st == THY_OK) {
+    chk(slq_eval(h, Pl, h->x.ptr, h->ll.ptr, h->lpr.ptr));
+    k_sub<<<(unsigned)ceil_div(Pl, 256), 256, 0, s>>>(Pl, h->ll.ptr, h->lpr.ptr, h->ll.ptr);
+    k_iota<<<(unsigned)ceil_div(Pl, 256), 256, 0, s>>>((int)Pl, h->idx_in.ptr);
+    std::vector<double> sc = {0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    chk(h->scalars.upload(sc, s));
+    std::vector<double> stt((size_t)h->A * 8, 0.0);
+    for (int a = 0; a < h->A; ++a) stt[(size_t)a * 8 + 5] = -INFINITY;
+    chk(h->abs_state.upload(stt, s));
+    count_launch(2);
+    if (cudaStreamSynchronize(s) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
+  }
+  if (st != THY_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return THY_OK;
+}
+
+thy_status thy_slq_destroy(thy_slq_t h) {
+  delete h;
+  return THY_OK;
+}
+
+// Live phase: rounds of "retire the K lowest, replace them above the threshold" until the reference's convergence test
+// (SlqEngine.scala:249-262: iterations > minIterationCount && iterations >= 10 P H) or maxIterationCount.
+static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* converged) {
+  cudaStream_t s = h->model->stream;
+  std::vector<double> ao((size_t)h->A * 2);
+  *converged = false;
+  for (long long r = 0; r < max_rounds; ++r) {
+    const long long remaining = (long long)h->cfg.maxIterationCount - h->iterations;
+    if (remaining <= 0) { *converged = true; break; }
+    const int Kr = (int)std::min<long long>(h->K, remaining);
+    int c = 0;
+    THY_TRY(slq_round(h, Kr, &c));
+    THY_CUDA_CHECK(cudaMemcpyAsync(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+    double hmax = -INFINITY;
+    for (int a = 0; a < h->A; ++a) hmax = std::max(hmax, ao[(size_t)a * 2 + 1]);
+    if (h->iterations > h->cfg.minIterationCount && std::isfinite(hmax) &&
+        (double)h->iterations >= 10.0 * (double)h->P * hmax) {
+      *converged = true;
+      break;
+    }
+  }
+  return THY_OK;
+}
+
+extern "C" thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (h->finished) return fail(THY_ERR_STATE, "the simulation has already been drained");
+  bool conv = false;
+  THY_TRY(slq_live_phase(h, n_rounds, &conv));
+  if (out_converged) *out_converged = conv ? 1 : 0;
+  return THY_OK;
+}
+
+extern "C" thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (h->finished) {
+    if (out_stats) *out_stats = h->stats;
+    return THY_OK;
+  }
+  cudaStream_t s = h->model->stream;
+  std::vector<double> ao((size_t)h->A * 2);
+  bool conv = false;
+  THY_TRY(slq_live_phase(h, (long long)1 << 60, &conv));
+  // drainSamplePool (SlqEngine.scala:171-180): the remaining live points in ascending order
+  THY_TRY(slq_sort_local(h));
+  const double* merged = h->keys_out.ptr;
+  if (h->world > 1) {
+    THY_TRY(comm_all_gather_f64(h->comm, h->keys_out.ptr, h->cand_all.ptr, (size_t)h->Pl, s));
+    THY_TRY(slq_sort_keys(h, h->cand_all.ptr, h->cand_sorted.ptr, (int)h->P));
+    merged = h->cand_sorted.ptr;
+  }
+  if (h->iterations + h->P > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, merged, (size_t)h->P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (h->cfg.keepRetiredPoints && h->world == 1) {
+    k_slq_store<<<(unsigned)ceil_div(h->Pl, 8), 256, 0, s>>>((int)h->Pl, h->d, h->idx_out.ptr, h->x.ptr,
+                                                            h->ret_x.ptr + (size_t)h->iterations * h->d);
+    count_launch();
+  }
+  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, (int)h->P, h->P, 1));
+  const long long live_iterations = h->iterations;
+  h->iterations += h->P;
+  std::vector<double> sc(8);
+  THY_CUDA_CHECK(cudaMemcpyAsync(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaMemcpyAsync(sc.data(), h->scalars.ptr, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  double minl = 0.0;
+  THY_CUDA_CHECK(cudaMemcpyAsync(&minl, h->ret_ll.ptr + live_iterations, sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  double mean = 0.0, m2 = 0.0, hm = 0.0;
+  for (int a = 0; a < h->A; ++a) {
+    mean += ao[(size_t)a * 2];
+    hm += ao[(size_t)a * 2 + 1];
+  }
+  mean /= h->A;
+  hm /= h->A;
+  for (int a = 0; a < h->A; ++a) m2 += (ao[(size_t)a * 2] - mean) * (ao[(size_t)a * 2] - mean);
+  h->stats.iterations = live_iterations;
+  h->stats.total_retired = h->iterations;
+  h->stats.rounds = h->rounds;
+  h->stats.log_evidence_mean = mean;
+  h->stats.log_evidence_std = h->A > 1 ? std::sqrt(m2 / (h->A - 1)) : 0.0;
+  h->stats.neg_entropy_mean = hm;
+  h->stats.min_logpdf = minl;
+  h->stats.walk_scale = sc[0];
+  h->stats.walk_acceptance = sc[6] > 0 ? sc[5] / sc[6] : 0.0;
+  h->stats.likelihood_evaluations = h->evals;
+  h->finished = true;
+  if (out_stats) *out_stats = h->stats;
+  return THY_OK;
+}
+
+/* Retired log-likelihoods in retirement order (live phase followed by the drained pool). */
+thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, int64_t* out_count) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  const long long n = std::min<long long>(max_count, h->iterations);
+  if (out_loglik && n > 0) {
+    THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
+    THY_CUDA_CHECK(cudaMemcpy(out_loglik, h->ret_ll.ptr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (out_count) *out_count = h->iterations;
+  return THY_OK;
+}
+
+/* Per-abscissa results of the quadrature so far: ln Z_a and H_a (QuadratureIntegrator.scala:29-62). */
+thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, double* out_neg_entropy) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  std::vector<double> ao((size_t)h->A * 2);
+  THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
+  THY_CUDA_CHECK(cudaMemcpy(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int a = 0; a < h->A; ++a) {
+    if (out_log_evidence) out_log_evidence[a] = ao[(size_t)a * 2];
+    if (out_neg_entropy) out_neg_entropy[a] = ao[(size_t)a * 2 + 1];
+  }
+  return THY_OK;
+}
+
+/* Posterior resampling of retired points (SamplingSimulation.scala:41-101) with weight w_i L_i under the expected
+ * abscissa E[ln X_i] = -sum 1/n_k.  Requires keepRetiredPoints (single GPU). */
+thy_status thy_slq_sample(thy_slq_t h, int n, uint64_t rng_seed, double* out_samples) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->finished) return fail(THY_ERR_STATE, "run the simulation first (rebuildSampleSimulation)");
+  if (!h->cfg.keepRetiredPoints || h->world != 1) return fail(THY_ERR_UNSUPPORTED, "retired points were not kept");
+  if (n <= 0 || !out_samples) return fail(THY_ERR_INVALID_ARGUMENT, "bad arguments");
+  const long long N = h->iterations;
+  std::vector<double> l((size_t)N);
+  THY_CUDA_CHECK(cudaMemcpy(l.data(), h->ret_ll.ptr, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+  // expected log X: live phase shrinks by 1/(P - j) within rounds of K, drain by 1/(P - j)
+  std::vector<double> lx((size_t)N);
+  double cur = 0.0;
+  const long long live = h->stats.iterations;
+  for (long long i = 0; i < N; ++i) {
+    lx[(size_t)i] = cur;
+    const long long j = (i < live) ? (i % h->K) : (i - live);
+    cur -= 1.0 / (double)(h->P - j);
+  }
+  std::vector<double> lw((size_t)N);
+  double mx = -INFINITY;
+  for (long long i = 0; i < N; ++i) {
+    const double hi = (i == 0) ? lx[0] : lx[(size_t)i - 1];
+    const double lo = (i + 1 < N) ? lx[(size_t)i + 1] : lx[(size_t)i];
+    const double gap = std::log(0.5) + hi + std::log(-std::expm1(lo - hi));
+    lw[(size_t)i] = l[(size_t)i] + gap;
+    mx = std::max(mx, lw[(size_t)i]);
+  }
+  std::vector<double> cdf((size_t)N);
+  double run = 0.0;
+  for (long long i = 0; i < N; ++i) {
+    run += std::exp(lw[(size_t)i] - mx);
+    cdf[(size_t)i] = run;
+  }
+  for (int k = 0; k < n; ++k) {
+    const RngDraw u = rng_uniform2(rng_seed, (uint64_t)k, 0, RNG_SLQ_PICK, 0xFFFFFFFFull);
+    const double target = u.u0 * run;
+    const long long idx = std::min<long long>(N - 1, std::upper_bound(cdf.begin(), cdf.end(), target) - cdf.begin());
+    THY_CUDA_CHECK(cudaMemcpy(out_samples + (size_t)k * h->d, h->ret_x.ptr + (size_t)idx * h->d, h->d * sizeof(double),
+                              cudaMemcpyDeviceToHost));
+  }
+  return THY_OK;
+}
+
+}  // extern "C"

@@ -220,3 +220,184 @@ class LeapfrogMcmcSampledPosterior:
         lp = np.empty(P)
         check(self._lib.thy_lfm_get_pool(self._h, _ptr(x), _ptr(lp)))
         return x, lp
+
+
+# ----------------------------------------------------------------------------------------------- moments
+register("thy_moments_reset_dev", C.c_int, [_vp, _vp])
+register("thy_moments_accumulate_dev", C.c_int, [_vp, C.c_int64, _vp, _vp])
+register("thy_moments_finish", C.c_int, [_vp, _vp, _vp, _dp, _dp, _dp])
+
+
+class SampleMoments:
+    """Device accumulator of (count, sum x, sum x x^T) over sample blocks; ``finish(comm)`` sums over the ranks
+    (NCCL all-reduce) and returns (count, mean, covariance).  Not in the reference."""
+
+    def __init__(self, posterior: UnnormalisedPosterior):
+        import torch
+        self.posterior = posterior
+        d = posterior.domainDimension
+        self._acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+        self._lib = lib()
+        check(self._lib.thy_moments_reset_dev(posterior.handle, self._acc.data_ptr()))
+
+    def add(self, x_dev) -> None:
+        """x_dev: CUDA fp64 tensor (..., d), contiguous; rows starting with NaN are skipped."""
+        assert x_dev.is_cuda and x_dev.is_contiguous() and x_dev.shape[-1] == self.posterior.domainDimension
+        n = x_dev.numel() // self.posterior.domainDimension
+        check(self._lib.thy_moments_accumulate_dev(self.posterior.handle, n, x_dev.data_ptr(), self._acc.data_ptr()))
+
+    def finish(self, comm=None):
+        d = self.posterior.domainDimension
+        cnt = C.c_double()
+        mean, cov = np.empty(d), np.empty((d, d))
+        check(self._lib.thy_moments_finish(self.posterior.handle, comm.handle if comm is not None else None,
+                                           self._acc.data_ptr(), C.byref(cnt), _ptr(mean), _ptr(cov)))
+        return cnt.value, mean, cov
+
+
+# --------------------------------------------------------------------------------------------------- SLQ
+class _SlqConfigC(C.Structure):
+    _fields_ = [("poolSize", C.c_int), ("abscissaNumber", C.c_int), ("domainScalingIncrement", C.c_double),
+                ("targetAcceptanceProbability", C.c_double), ("sampleParallelism", C.c_int),
+                ("maxIterationCount", C.c_int), ("minIterationCount", C.c_int), ("constrainedWalkSteps", C.c_int),
+                ("keepRetiredPoints", C.c_int)]
+
+
+class _SlqStatsC(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("total_retired", C.c_int64), ("rounds", C.c_int64),
+                ("likelihood_evaluations", C.c_int64), ("log_evidence_mean", C.c_double),
+                ("log_evidence_std", C.c_double), ("neg_entropy_mean", C.c_double), ("min_logpdf", C.c_double),
+                ("walk_scale", C.c_double), ("walk_acceptance", C.c_double)]
+
+
+register("thy_slq_create", C.c_int, [_vp, C.POINTER(_SlqConfigC), C.c_uint64, _dp, C.c_int, _vp, C.POINTER(_vp)])
+register("thy_slq_destroy", C.c_int, [_vp])
+register("thy_slq_run", C.c_int, [_vp, C.POINTER(_SlqStatsC)])
+register("thy_slq_run_rounds", C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)])
+register("thy_slq_retired", C.c_int, [_vp, C.c_int64, _dp, _i64p])
+register("thy_slq_sample", C.c_int, [_vp, C.c_int, C.c_uint64, _dp])
+register("thy_slq_abscissa_results", C.c_int, [_vp, _dp, _dp])
+
+
+@dataclass
+class SlqConfig:
+    """config/SlqConfig.scala:20-28"""
+    poolSize: int
+    abscissaNumber: int
+    domainScalingIncrement: float
+    targetAcceptanceProbability: float
+    sampleParallelism: int
+    maxIterationCount: int
+    minIterationCount: int
+
+
+@dataclass
+class SlqTelemetryUpdate:
+    """core/telemetry/SlqTelemetryUpdate.scala:20-29 (domainCubeCount has no analogue: there is no cubical cover)"""
+    negEntropyAvg: float
+    logPdf: float
+    samplePoolMinimumLogPdf: float
+    domainVolumeScaling: float
+    acceptancesSinceDomainRebuild: int
+    samplePoolSize: int
+    domainCubeCount: int
+    iterationCount: int
+
+
+class SlqIntegratedPosterior:
+    """``SlqIntegratedPosterior.of(slqConfig, posterior, slqTelemetryUpdateCallback, domainRebuildStartCallback,
+    domainRebuildFinishCallback, seedsSpec)`` (components/posterior/SlqIntegratedPosterior.scala:87-125) followed by
+    ``rebuildSampleSimulation`` (:76-80), ``logEvidence`` / ``integrate`` and ``sample`` (SlqEngine.scala:460-469).
+
+    Re-designed for 10^6 live points (DESIGN.md "SLQ"): K = sampleParallelism points are retired per round; their
+    replacements are constrained random walks from surviving live points; the threshold is selected on the device
+    and, across GPUs, with one NCCL all-gather per round.  ``comm`` shards the live points across ranks."""
+
+    def __init__(self, *a, **k):
+        raise TypeError("use SlqIntegratedPosterior.of(...), as in the reference")
+
+    @classmethod
+    def of(cls, slqConfig: SlqConfig, posterior: UnnormalisedPosterior, slqTelemetryUpdateCallback=None,
+           domainRebuildStartCallback=None, domainRebuildFinishCallback=None, seedsSpec=None, rngSeed: int = 0,
+           comm=None, constrainedWalkSteps: int = 0, keepRetiredPoints: bool = False):
+        self = object.__new__(cls)
+        self.posterior, self.config, self.comm = posterior, slqConfig, comm
+        self._cb = slqTelemetryUpdateCallback
+        self._lib = lib()
+        cfg = _SlqConfigC(slqConfig.poolSize, slqConfig.abscissaNumber, float(slqConfig.domainScalingIncrement),
+                          float(slqConfig.targetAcceptanceProbability), slqConfig.sampleParallelism,
+                          slqConfig.maxIterationCount, slqConfig.minIterationCount, int(constrainedWalkSteps),
+                          1 if keepRetiredPoints else 0)
+        seeds = None
+        n_seeds = 0
+        if seedsSpec:
+            rows = [posterior.flatten(s) if isinstance(s, Mapping) else _arr(s) for s in seedsSpec]
+            seeds = np.ascontiguousarray(np.stack(rows))
+            n_seeds = seeds.shape[0]
+        h = C.c_void_p()
+        check(self._lib.thy_slq_create(posterior.handle, C.byref(cfg), rngSeed, _ptr(seeds) if seeds is not None else None,
+                                       n_seeds, comm.handle if comm is not None else None, C.byref(h)))
+        self._h = h
+        self.stats: Optional[_SlqStatsC] = None
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.thy_slq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rebuildSampleSimulation(self) -> None:
+        st = _SlqStatsC()
+        check(self._lib.thy_slq_run(self._h, C.byref(st)))
+        self.stats = st
+        if self._cb is not None:
+            self._cb(SlqTelemetryUpdate(st.neg_entropy_mean, st.min_logpdf, st.min_logpdf, st.walk_scale, 0,
+                                        self.config.poolSize, 0, int(st.iterations)))
+
+    def runRounds(self, n: int) -> bool:
+        conv = C.c_int()
+        check(self._lib.thy_slq_run_rounds(self._h, n, C.byref(conv)))
+        return bool(conv.value)
+
+    @property
+    def logEvidence(self) -> float:
+        """Mean over the abscissas of ln Z (calibrated: prior-measure nested sampling)."""
+        assert self.stats is not None, "call rebuildSampleSimulation first"
+        return self.stats.log_evidence_mean
+
+    def abscissaResults(self):
+        lz, hh = np.empty(self.config.abscissaNumber), np.empty(self.config.abscissaNumber)
+        check(self._lib.thy_slq_abscissa_results(self._h, _ptr(lz), _ptr(hh)))
+        return lz, hh
+
+    def retiredLogLikelihoods(self) -> np.ndarray:
+        n = C.c_int64()
+        check(self._lib.thy_slq_retired(self._h, 0, None, C.byref(n)))
+        out = np.empty(n.value)
+        check(self._lib.thy_slq_retired(self._h, n.value, _ptr(out), C.byref(n)))
+        return out
+
+    def integrate(self, integrand: Callable[[np.ndarray], np.ndarray]) -> float:
+        """QuadratureIntegrator.getIntegrationStats (QuadratureIntegrator.scala:64-83) under the expected abscissa:
+        sum_i w_i integrand(L_i) with L_i = exp(l_i - max l).  ``integrand`` maps an array of scaled likelihoods."""
+        ll = self.retiredLogLikelihoods()
+        P, K, live = self.config.poolSize, max(1, min(self.config.sampleParallelism, self.config.poolSize // 4)), int(self.stats.iterations)
+        j = np.where(np.arange(ll.size) < live, np.arange(ll.size) % K, np.arange(ll.size) - live)
+        lx = np.concatenate([[0.0], np.cumsum(-1.0 / (P - j))])[:-1]
+        X = np.exp(lx)
+        w = np.empty_like(X)
+        w[1:-1] = 0.5 * (X[:-2] - X[2:])
+        w[0] = 0.5 * (X[0] - X[1])
+        w[-1] = 0.5 * (X[-2] - X[-1])
+        return float(np.sum(w * integrand(np.exp(ll - ll.max()))))
+
+    def sample(self, numberOfSamples: int, rngSeed: int = 1) -> List[Dict[str, np.ndarray]]:
+        out = np.empty((numberOfSamples, self.posterior.domainDimension))
+        check(self._lib.thy_slq_sample(self._h, numberOfSamples, rngSeed, _ptr(out)))
+        return [self.posterior.unflatten(x) for x in out]
