@@ -127,6 +127,22 @@ def test_slq_linear_model_gaussian_prior_and_posterior_samples():
     assert abs(got - want) < tol + 0.05
 
 
+def test_slq_duplicate_live_points_do_not_break_the_threshold_step():
+    """A walker that never moves is an exact copy of a survivor (the reference nudges duplicates by one ulp,
+    SlqEngine.scala:107-118); with one walk step per replacement most replacements are copies, so log-likelihood ties
+    straddle the threshold constantly.  Exactly K points must still be retired per round."""
+    post, _, _ = _identity_model(8, seed=3)
+    P, K = 4096, 1024
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=2, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                      sampleParallelism=K, maxIterationCount=60 * K, minIterationCount=60 * K)
+    slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=17, constrainedWalkSteps=1)
+    slq.rebuildSampleSimulation()
+    ll = slq.retiredLogLikelihoods()
+    assert slq.stats.iterations == 60 * K and ll.size == 61 * K + (P - K)
+    assert np.all(np.diff(ll) >= 0)
+    assert np.sum(np.diff(ll) == 0) > 0, "the scenario is meant to produce ties"
+
+
 def test_slq_argument_checks_and_call_order():
     post, _, _ = _identity_model(2, seed=1)
     bad = t.SlqConfig(poolSize=2, abscissaNumber=1, domainScalingIncrement=0.1, targetAcceptanceProbability=0.3,

@@ -68,18 +68,46 @@ __global__ void k_fill(long long n, double* v, double val) {
   if (i < n) v[i] = val;
 }
 
-// threshold = merged[Kr-1]; local retire count = #sorted local keys <= threshold
+// threshold = merged[Kr-1].  Exactly Kr points are retired globally even when log-likelihoods tie (a walker that never
+// moved is an exact copy of a survivor; the reference nudges duplicates by one ulp instead, SlqEngine.scala:107-118):
+// every value < threshold goes, and the ties at the threshold are taken in rank order, lowest sorted index first.
+__device__ __forceinline__ long long lower_bound_dev(const double* v, long long n, double x) {  // first index with v >= x
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (v[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ long long upper_bound_dev(const double* v, long long n, double x) {  // first index with v > x
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (v[mid] <= x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 __global__ void k_slq_threshold(const double* __restrict__ merged, int Kr, const double* __restrict__ local_sorted,
-                                long long Pl, double* __restrict__ scalars, int* __restrict__ count) {
+                                const double* __restrict__ cand_all, int world, int rank,
+                                double* __restrict__ scalars, int* __restrict__ count) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double thr = merged[Kr - 1];
   scalars[1] = thr;
-  long long lo = 0, hi = Pl;  // first index with key > thr
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (local_sorted[mid] <= thr) lo = mid + 1; else hi = mid;
+  if (world == 1) {
+    count[0] = Kr;
+    return;
   }
-  count[0] = (int)lo;
+  const long long below = lower_bound_dev(merged, (long long)Kr * world, thr);
+  long long need = Kr - below;  // ties still to take, >= 1
+  long long mine = 0;
+  for (int r = 0; r <= rank; ++r) {
+    const double* cr = cand_all + (size_t)r * Kr;
+    const long long ties = upper_bound_dev(cr, Kr, thr) - lower_bound_dev(cr, Kr, thr);
+    const long long take = ties < need ? ties : need;
+    if (r == rank) mine = take;
+    need -= take;
+  }
+  count[0] = (int)(lower_bound_dev(local_sorted, Kr, thr) + mine);
 }
 
 // Per-dimension standard deviation of the live pool: deterministic two-stage reduction.
@@ -388,7 +416,8 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
     THY_TRY(slq_sort_keys(h, h->cand_all.ptr, h->cand_sorted.ptr, Kr * h->world));
     merged = h->cand_sorted.ptr;
   }
-  k_slq_threshold<<<1, 32, 0, s>>>(merged, Kr, h->keys_out.ptr, h->Pl, h->scalars.ptr, h->count_dev.ptr);
+  k_slq_threshold<<<1, 32, 0, s>>>(merged, Kr, h->keys_out.ptr, h->cand_all.ptr, h->world, h->rank, h->scalars.ptr,
+                                   h->count_dev.ptr);
   count_launch();
   int c = 0;
   THY_CUDA_CHECK(cudaMemcpyAsync(&c, h->count_dev.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -397,6 +426,7 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
   THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, merged, (size_t)Kr * sizeof(double), cudaMemcpyDeviceToDevice, s));
   THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, Kr, h->P, 0));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (c > h->K) return fail(THY_ERR_STATE, "SLQ: internal error, retire count exceeds the walker buffers");
   if (c >= h->Pl) return fail(THY_ERR_STATE, "SLQ: a rank lost all of its live points in one round; lower sampleParallelism");
   if (h->cfg.keepRetiredPoints && h->world == 1 && c > 0) {
     k_slq_store<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->idx_out.ptr, h->x.ptr, h->ret_x.ptr + (size_t)h->iterations * d);
