@@ -297,3 +297,71 @@ def test_full_size_config2_properties():
     quad = -0.5 * np.einsum("bi,ij,bj->b", D, lam, D)
     assert np.max(np.abs((lp - lp0[0]) - quad)) < 1e-9 * np.max(np.abs(quad)) + 1e-7
     assert np.max(np.abs(g + D @ lam)) < 1e-9 * gscale                        # grad = -Lambda (x - mu)
+
+
+# ---- small-batch streaming kernel (B <= 8): TMA-staged memory-bound pass -----------------------------------
+STREAM_SHAPES = [(1, 1, 1), (3, 5, 2), (10, 1000, 1), (10, 1000, 8), (31, 64, 3), (32, 33, 4), (33, 257, 5), (64, 4000, 7),
+                 (100, 10_000, 1), (100, 10_000, 6), (128, 300, 8), (97, 20_000, 2)]
+
+
+@pytest.mark.parametrize("d,n,B", STREAM_SHAPES)
+def test_stream_kernel_linear_gaussian(d, n, B):
+    prob = linear_gaussian_problem(d, n, seed=77 + d + n)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")],
+                                   kernelPath=capi.KERNEL_STREAM)
+    rng = np.random.default_rng(B)
+    for X in (typical_set_points(prob, B, seed=B) if n >= d else rng.standard_normal((B, d)),
+              prob["pm"] + 10.0 * rng.standard_normal((B, d))):
+        want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
+                                                  prior_var=prob["pvar"])
+        lp, g = post.logPdfGradBatch(X)
+        assert post.lastKernelPath == "stream"
+        assert rel_err_logp(lp, want_lp) < TOL
+        assert rel_err_grad(g, want_g) < TOL
+        lp2, g2 = post.logPdfGradBatch(X)                       # deterministic, and the ticket was reset
+        assert np.array_equal(lp, lp2) and np.array_equal(g, g2)
+        assert rel_err_logp(post.logPdfBatch(X), want_lp) < TOL
+
+
+def test_stream_kernel_is_the_small_batch_default_and_rejects_large_batches():
+    prob = linear_gaussian_problem(20, 500, seed=9)
+    pri = [t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])]
+    lik = [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")]
+    auto = t.UnnormalisedPosterior(pri, lik)
+    auto.logPdfGradBatch(typical_set_points(prob, 4, seed=1))
+    assert auto.lastKernelPath == "stream"
+    auto.logPdfGradBatch(typical_set_points(prob, 40, seed=1))
+    assert auto.lastKernelPath == "fused_dmma"
+    forced = t.UnnormalisedPosterior(pri, lik, kernelPath=capi.KERNEL_STREAM)
+    X = typical_set_points(prob, 27, seed=1)                   # 4 groups of <= 8 chains, one pass over A each
+    lp, g = forced.logPdfGradBatch(X)
+    want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"], prior_var=prob["pvar"])
+    assert forced.lastKernelPath == "stream" and rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
+    with pytest.raises(t.ThylacineError) as e:
+        forced.logPdfGradBatch(typical_set_points(prob, 33, seed=1))
+    assert e.value.status == capi.THY_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("faithful", [True, False])
+def test_stream_kernel_cauchy_multi_label_offset(faithful):
+    rng = np.random.default_rng(21)
+    n = 90
+    A = {"gamma": rng.standard_normal((n, 2)), "alpha": rng.standard_normal((n, 3))}
+    off, y = rng.standard_normal(n), rng.standard_normal(n)
+    ci = 0.5 + rng.random(n)
+    pri = [t.GaussianPrior.fromConfidenceIntervals("alpha", np.zeros(3), np.full(3, 4.0)),
+           t.UniformPrior.fromBounds("beta", np.full(4, 9.0), np.full(4, -9.0)),
+           t.GaussianPrior.fromConfidenceIntervals("gamma", np.ones(2), np.full(2, 2.0))]
+    lik = t.CauchyLikelihood(t.LinearForwardModel.of(transform=A, vectorOffset=off), y, ci)
+    post = t.UnnormalisedPosterior(pri, [lik], cauchyReferenceSign=faithful, kernelPath=capi.KERNEL_STREAM)
+    ref = o.Posterior([o.gaussian_prior_from_ci("alpha", np.zeros(3), np.full(3, 4.0)),
+                       o.uniform_prior_from_bounds("beta", np.full(4, 9.0), np.full(4, -9.0)),
+                       o.gaussian_prior_from_ci("gamma", np.ones(2), np.full(2, 2.0))],
+                      [o.cauchy_likelihood(o.LinearForwardModel(A, off), y, ci, reference_faithful=faithful)])
+    X = rng.standard_normal((5, 9))
+    lp, g = post.logPdfGradBatch(X)
+    assert post.lastKernelPath == "stream"
+    for b in range(5):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL

@@ -24,7 +24,8 @@ thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* lo
     if (path == 3 && !(linear && stream_supported(lk, B)))
       return fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
     if (path == 0) {
-      if (linear && stream_supported(lk, B) && B <= 16)
+      if (linear && stream_supported(lk, B) &&
+          (!fused_dmma_supported(lk, grad != nullptr) || stream_cost_model(lk, B) <= fused_cost_model(lk, B)))
         path = 3;
       else if (linear && fused_dmma_supported(lk, grad != nullptr))
         path = 2;

@@ -15,11 +15,13 @@ thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int
 // kernels_fused_dmma.cu -- linear forward model + Gaussian/Cauchy observations, fused forward/residual/adjoint
 int fused_nt_for(int dl);  // 0 when the width is not covered by the fused kernel
 bool fused_dmma_supported(const LikDev& lik, bool want_grad);
+double fused_cost_model(const LikDev& lik, int64_t B);    // seconds, for auto-selection
 thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
                              double cauchy_sign, cudaStream_t s);
 
 // kernels_stream.cu -- small-batch memory-bound pass (A streamed once per batch)
 bool stream_supported(const LikDev& lik, int64_t B);
+double stream_cost_model(const LikDev& lik, int64_t B);   // seconds, for auto-selection
 thy_status launch_stream(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
                          double cauchy_sign, cudaStream_t s);
 

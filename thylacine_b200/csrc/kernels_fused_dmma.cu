@@ -324,6 +324,13 @@ bool fused_dmma_supported(const LikDev& lik, bool want_grad) {
   return nt > 0 && lik.lds == 8 * nt + 4 && lik.n_pad % MB == 0;
 }
 
+// Auto-selection cost model (seconds): whole 64-chain tiles at ~30 TFLOP/s, plus the finish kernel.
+double fused_cost_model(const LikDev& lik, int64_t B) {
+  const double flops = 4.0 * lik.n_pad * (lik.lds - 4) * 64.0 * (double)((B + 63) / 64);
+  const double t = flops / 30e12;
+  return 5e-6 + (t > 6e-6 ? t : 6e-6);
+}
+
 thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
                              double cauchy_sign, cudaStream_t s) {
   const LikDev& lk = lik.view;

@@ -75,6 +75,7 @@ struct Workspace {  // grow-only scratch owned by the model, reused across evalu
   DevBuf<double> W;                     // generic path: weighted residuals [B][n_pad]
   DevBuf<double> partG, partL;          // stream-K partial tiles
   DevBuf<double> Z;                     // generic path scratch
+  DevBuf<unsigned int> ticket;          // streaming kernel: last-CTA ticket, zero between launches
 };
 
 }  // namespace thy

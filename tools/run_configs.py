@@ -192,6 +192,37 @@ def c5(t, torch, out, d=200, n=256, B=16384, L=8):
     out["c5_nonlinear_cauchy_fd_200d"] = res
 
 
+def stream(t, torch, out, d=100, n=1_000_000):
+    """Small-batch streaming kernel against the HBM roofline: A (8 n d bytes = 800 MB >> L2) read once per launch."""
+    import ctypes as C
+    A, theta, y = linear_problem(d, n, 20260106)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.full(d, 20.0))],
+                                   [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.2), "theta")])
+    stream_ = torch.cuda.Stream()
+    post.setStream(stream_.cuda_stream)
+    L = t.lib()
+    res = {}
+    for B in (1, 2, 4, 8, 16):
+        X = torch.from_numpy(theta[None, :] + 0.01 * np.random.default_rng(B).standard_normal((B, d))).cuda()
+        lp = torch.empty(B, dtype=torch.float64, device="cuda")
+        g = torch.empty(B, d, dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            post.logPdfGradBatchDevice(B, X.data_ptr(), lp.data_ptr(), g.data_ptr())
+        post.synchronize()
+        L.thy_model_enable_timing(post.handle, 1)
+        reps = 20
+        dt = timed(lambda: [post.logPdfGradBatchDevice(B, X.data_ptr(), lp.data_ptr(), g.data_ptr()) for _ in range(reps)],
+                   post.synchronize)
+        k_ms, k_n = C.c_double(), C.c_int64()
+        L.thy_model_kernel_time(post.handle, C.byref(k_ms), C.byref(k_n))
+        L.thy_model_enable_timing(post.handle, 0)
+        kms = k_ms.value / max(k_n.value, 1)
+        res[f"B{B}"] = {"kernel_path": post.lastKernelPath, "kernel_ms": kms, "wall_ms_per_eval_batch": 1e3 * dt / reps,
+                        "algorithmic_GBps": 8.0 * n * d / (kms * 1e-3) / 1e9, "evals_per_s": B * reps / dt}
+    out["stream_100d_1M_obs"] = res
+    post.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="c1,c2hmc,c3,c4,c5")
@@ -200,7 +231,7 @@ def main():
     import torch
     import thylacine_b200 as t
     out = {"gpu": torch.cuda.get_device_name(0), "host_cores": os.cpu_count()}
-    fns = {"c1": c1, "c2hmc": c2hmc, "c3": c3, "c4": c4, "c5": c5}
+    fns = {"c1": c1, "c2hmc": c2hmc, "c3": c3, "c4": c4, "c5": c5, "stream": stream}
     for name in args.only.split(","):
         t0 = time.perf_counter()
         try:
