@@ -118,7 +118,8 @@ typedef enum thy_option {
    * forward model (the reference's arithmetic); 1 = incremental z + h A[:,j] (same limit, fewer flops).   */
   THY_OPT_FD_INCREMENTAL = 1,
   /* Kernel selection for linear-Gaussian terms: 0 = auto, 1 = force generic tiled kernels,
-   * 2 = force fused DMMA kernel (error if the shape is unsupported), 3 = force streaming (small-batch) kernel. */
+   * 2 = force fused DMMA kernel (error if the shape is unsupported), 3 = force streaming (small-batch) kernel,
+   * 4 = force the wide DMMA GEMM pair (any width / link; not for uniform observations or FD Jacobians).      */
   THY_OPT_KERNEL_PATH = 2
 } thy_option;
 thy_status thy_model_set_option(thy_model_t m, int option, int value);

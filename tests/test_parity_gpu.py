@@ -365,3 +365,72 @@ def test_stream_kernel_cauchy_multi_label_offset(faithful):
     for b in range(5):
         assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
         assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+# ---- wide DMMA GEMM path: d > 128 and / or non-linear links on the tensor cores -----------------------------
+WIDE_SHAPES = [(200, 300, 150), (129, 129, 64), (1000, 517, 130), (333, 1000, 257), (7, 60, 33), (64, 5, 40), (100, 1000, 129)]
+
+
+@pytest.mark.parametrize("d,n,B", WIDE_SHAPES)
+def test_wide_path_linear_gaussian(d, n, B):
+    prob = linear_gaussian_problem(d, n, seed=500 + d + n)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")],
+                                   kernelPath=capi.KERNEL_WIDE)
+    rng = np.random.default_rng(B)
+    for X in (typical_set_points(prob, B, seed=B) if n >= d else rng.standard_normal((B, d)),
+              prob["pm"] + 10.0 * rng.standard_normal((B, d))):
+        want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
+                                                  prior_var=prob["pvar"])
+        lp, g = post.logPdfGradBatch(X)
+        assert post.lastKernelPath == "wide_dmma"
+        assert rel_err_logp(lp, want_lp) < TOL
+        assert rel_err_grad(g, want_g) < TOL
+        assert rel_err_logp(post.logPdfBatch(X), want_lp) < TOL           # value only: W is never written
+        lp2, g2 = post.logPdfGradBatch(X)
+        assert np.array_equal(lp, lp2) and np.array_equal(g, g2)          # deterministic
+
+
+def test_wide_path_is_the_default_beyond_128_columns():
+    prob = linear_gaussian_problem(160, 400, seed=4)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
+    post.logPdfGradBatch(typical_set_points(prob, 64, seed=1))
+    assert post.lastKernelPath == "wide_dmma"
+    post.logPdfGradBatch(typical_set_points(prob, 3, seed=1))
+    assert post.lastKernelPath == "generic"
+
+
+@pytest.mark.parametrize("link", ["tanh", "softplus", "identity"])
+@pytest.mark.parametrize("faithful", [True, False])
+def test_wide_path_cauchy_links_multi_label_offset(link, faithful):
+    rng = np.random.default_rng(31)
+    n, B = 210, 140
+    dims = {"alpha": 70, "beta": 40, "gamma": 90}
+    A = {"gamma": rng.standard_normal((n, 90)) / 10, "alpha": rng.standard_normal((n, 70)) / 10}   # skips beta
+    off = 0.1 * rng.standard_normal(n)
+    fn = {"tanh": np.tanh, "softplus": lambda z: np.logaddexp(0, z), "identity": lambda z: z}[link]
+    dfn = {"tanh": lambda z: 1 - np.tanh(z) ** 2, "softplus": lambda z: 1 / (1 + np.exp(-z)), "identity": np.ones_like}[link]
+    y = fn(rng.standard_normal(n)) + 0.05 * rng.standard_normal(n)
+    ci = rng.uniform(1.5, 2.5, n)      # keeps the reference's det / Gamma normaliser finite at n = 210
+    pri = [t.GaussianPrior.fromConfidenceIntervals(k, np.zeros(w), np.full(w, 4.0)) for k, w in dims.items()]
+    fm = (t.LinearForwardModel.of(transform=A, vectorOffset=off) if link == "identity"
+          else t.NonLinearForwardModel.of(link, A, vectorOffset=off))
+    post = t.UnnormalisedPosterior(pri, [t.CauchyLikelihood(fm, y, ci)], cauchyReferenceSign=faithful,
+                                   kernelPath=capi.KERNEL_WIDE)
+    Acat = np.concatenate([A["alpha"], A["gamma"]], axis=1)
+
+    def pre(p):
+        return Acat @ np.concatenate([p["alpha"], p["gamma"]]) + off
+    ofm = o.NonLinearForwardModel(lambda p: fn(pre(p)), None, dims, n,
+                                  jacobian=lambda p: {"alpha": dfn(pre(p))[:, None] * A["alpha"],
+                                                      "beta": np.zeros((n, 40)),
+                                                      "gamma": dfn(pre(p))[:, None] * A["gamma"]})
+    ref = o.Posterior([o.gaussian_prior_from_ci(k, np.zeros(w), np.full(w, 4.0)) for k, w in dims.items()],
+                      [o.cauchy_likelihood(ofm, y, ci, faithful)])
+    X = 0.5 * rng.standard_normal((B, 200))
+    lp, g = post.logPdfGradBatch(X)
+    assert post.lastKernelPath == "wide_dmma"
+    for b in range(0, B, 7):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL

@@ -23,7 +23,7 @@ DIST_GAUSSIAN, DIST_CAUCHY, DIST_UNIFORM = 0, 1, 2
 LINK_IDENTITY, LINK_TANH, LINK_EXP, LINK_SQUARE, LINK_SOFTPLUS, LINK_SIGMOID = range(6)
 JAC_CONSTANT, JAC_ANALYTIC, JAC_FINITE_DIFFERENCE = 0, 1, 2
 OPT_CAUCHY_REFERENCE_SIGN, OPT_FD_INCREMENTAL, OPT_KERNEL_PATH = 0, 1, 2
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED_DMMA, KERNEL_STREAM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED_DMMA, KERNEL_STREAM, KERNEL_WIDE = 0, 1, 2, 3, 4
 
 
 class ThylacineError(RuntimeError):

@@ -23,12 +23,16 @@ thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* lo
       return fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
     if (path == 3 && !(linear && stream_supported(lk, B)))
       return fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
+    if (path == 4 && !wide_supported(lk))
+      return fail(THY_ERR_UNSUPPORTED, "wide DMMA path does not support this likelihood (uniform observations / FD Jacobian)");
     if (path == 0) {
       if (linear && stream_supported(lk, B) &&
           (!fused_dmma_supported(lk, grad != nullptr) || stream_cost_model(lk, B) <= fused_cost_model(lk, B)))
         path = 3;
       else if (linear && fused_dmma_supported(lk, grad != nullptr))
         path = 2;
+      else if (wide_supported(lk) && B >= 32 && (long long)lk.n * lk.dl >= 4096)
+        path = 4;
       else
         path = 1;
     }
@@ -38,6 +42,9 @@ thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* lo
     } else if (path == 3) {
       m->last_path = "stream";
       THY_TRY(launch_stream(m, *own, B, X, logp, grad, csign, s));
+    } else if (path == 4) {
+      m->last_path = "wide_dmma";
+      THY_TRY(launch_wide_likelihood(m, *own, B, X, logp, grad, csign, s));
     } else {
       m->last_path = "generic";
       THY_TRY(launch_generic_likelihood(m, *own, B, X, logp, grad, csign, s));

@@ -25,6 +25,11 @@ double stream_cost_model(const LikDev& lik, int64_t B);   // seconds, for auto-s
 thy_status launch_stream(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
                          double cauchy_sign, cudaStream_t s);
 
+// kernels_wide.cu -- any width / any link on the fp64 tensor cores (two tiled DMMA GEMMs, W materialised in tiled form)
+bool wide_supported(const LikDev& lik);
+thy_status launch_wide_likelihood(thy_model_s* m, LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
+                                  double cauchy_sign, cudaStream_t s);
+
 // link functions (device), shared by the generic and FD kernels
 __device__ __forceinline__ double link_eval(int link, double z) {
   switch (link) {
@@ -43,6 +48,19 @@ __device__ __forceinline__ double link_deriv(int link, double z) {
     case THY_LINK_SQUARE: return 2.0 * z;
     case THY_LINK_SOFTPLUS: return 1.0 / (1.0 + exp(-z));
     case THY_LINK_SIGMOID: { double s = 1.0 / (1.0 + exp(-z)); return s * (1.0 - s); }
+    default: return 1.0;
+  }
+}
+
+// derivative of the link given both the pre-activation z and the value f = link(z) already in hand
+// (saves the second transcendental: tanh' = 1 - f^2, exp' = f, sigmoid' = f (1 - f))
+__device__ __forceinline__ double link_deriv_from(int link, double z, double f) {
+  switch (link) {
+    case THY_LINK_TANH: return 1.0 - f * f;
+    case THY_LINK_EXP: return f;
+    case THY_LINK_SQUARE: return 2.0 * z;
+    case THY_LINK_SOFTPLUS: return 1.0 / (1.0 + exp(-z));
+    case THY_LINK_SIGMOID: return f * (1.0 - f);
     default: return 1.0;
   }
 }

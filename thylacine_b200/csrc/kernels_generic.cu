@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) k_fwd_generic(LikDev lk, int d, long long
             const double res = yv.x - f;
             w = res * yv.y;
             s += res * w;
-            if (write_deriv) w *= link_deriv(lk.link, z);
+            if (write_deriv) w *= link_deriv_from(lk.link, z, f);
           }
         }
         W[b * lk.n_pad + i] = w;
@@ -184,43 +184,71 @@ __global__ void __launch_bounds__(256) k_adj_generic(LikDev lk, int d, long long
 // (the unperturbed one is Z from the forward kernel).  grad_j = sum_i w_i (f(theta + h e_j)_i - f(theta)_i) (1/h).
 // incremental = 0: the perturbed pre-activation is recomputed from the nudged parameter vector (literal);
 // incremental = 1: z + A[:,j] * ((theta_j + h) - theta_j)  (exact-arithmetic equal, one rounding instead of dl).
+constexpr int FD_TI = 1024;  // observation rows staged per shared-memory tile
+
 __global__ void __launch_bounds__(128) k_fd_adjoint(LikDev lk, int d, long long B, const double* __restrict__ X,
                                                     const double* __restrict__ W, const double* __restrict__ Z,
                                                     const double* __restrict__ scale, double* __restrict__ grad,
                                                     int incremental) {
-  extern __shared__ double sh[];  // theta[dl] for this chain
+  extern __shared__ double sh[];  // theta[dl] | z0[FD_TI] | f0[FD_TI] | w[FD_TI]
+  double* zs = sh + lk.dl;
+  double* fs = zs + FD_TI;
+  double* ws = fs + FD_TI;
   const long long b = blockIdx.x;
   if (b >= B) return;
   for (int k = threadIdx.x; k < lk.dl; k += blockDim.x) sh[k] = X[b * d + lk.col[k]];
   __syncthreads();
   const int j = blockIdx.y * blockDim.x + threadIdx.x;
-  if (j >= lk.dl) return;
+  const bool active = j < lk.dl;
   const double h = lk.differential;
   const double inv_h = 1 / h;
-  const double nudged = sh[j] + h;
-  const double dj = nudged - sh[j];
+  const double nudged = active ? sh[j] + h : 0.0;
+  const double dj = active ? nudged - sh[j] : 0.0;
   double acc = 0.0;
-  for (int i = 0; i < lk.n; ++i) {
-    double z0, z1;
+  for (int i0 = 0; i0 < lk.n; i0 += FD_TI) {
+    const int ni = (lk.n - i0 < FD_TI) ? (lk.n - i0) : FD_TI;
     if (incremental) {
-      z0 = Z[b * lk.n_pad + i];
-      z1 = fma(lk.A[(size_t)i * lk.lds + j], dj, z0);
-    } else {
-      // both evaluations through the same summation order, as the reference's closure would
-      const double* arow = lk.A + (size_t)i * lk.lds;
-      double s0 = 0.0, s1 = 0.0;
-      for (int k = 0; k < lk.dl; ++k) {
-        const double a = arow[k];
-        s0 = fma(a, sh[k], s0);
-        s1 = fma(a, (k == j) ? nudged : sh[k], s1);
+      // the unperturbed model f(theta) is evaluated once per observation and shared by all perturbed coordinates
+      for (int i = threadIdx.x; i < ni; i += blockDim.x) {
+        const double z0 = Z[b * lk.n_pad + i0 + i];
+        zs[i] = z0;
+        fs[i] = link_eval(lk.link, z0);
+        ws[i] = W[b * lk.n_pad + i0 + i];
       }
-      z0 = s0 + lk.off[i];
-      z1 = s1 + lk.off[i];
+      __syncthreads();
+      if (active) {
+        for (int i = 0; i < ni; ++i) {
+          const double z1 = fma(lk.A[(size_t)(i0 + i) * lk.lds + j], dj, zs[i]);
+          const double jac = (link_eval(lk.link, z1) - fs[i]) * inv_h;
+          acc = fma(ws[i], jac, acc);
+        }
+      }
+      __syncthreads();
+    } else if (active) {
+      for (int i = i0; i < i0 + ni; ++i) {
+        // both evaluations through the same summation order, as the reference's closure would
+        const double* arow = lk.A + (size_t)i * lk.lds;
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < lk.dl; ++k) {
+          const double a = arow[k];
+          s0 = fma(a, sh[k], s0);
+          s1 = fma(a, (k == j) ? nudged : sh[k], s1);
+        }
+        const double z0 = s0 + lk.off[i];
+        const double z1 = s1 + lk.off[i];
+        const double jac = (link_eval(lk.link, z1) - link_eval(lk.link, z0)) * inv_h;
+        acc = fma(W[b * lk.n_pad + i], jac, acc);
+      }
     }
-    const double jac = (link_eval(lk.link, z1) - link_eval(lk.link, z0)) * inv_h;
-    acc = fma(W[b * lk.n_pad + i], jac, acc);
   }
-  grad[b * d + lk.col[j]] += scale[b] * acc;
+  if (active) grad[b * d + lk.col[j]] += scale[b] * acc;
+}
+
+thy_status launch_finish_generic(const LikDev& lk, long long B, const double* partS, int n_tiles, double* logp, double* scale,
+                                 double cauchy_sign, cudaStream_t s) {
+  k_finish_generic<<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(lk, B, partS, n_tiles, logp, scale, cauchy_sign);
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
 }
 
 thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp,
@@ -251,7 +279,10 @@ thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int
     if (want_adj) {
       if (fd) {
         dim3 ga((unsigned)nb, (unsigned)ceil_div(lk.dl, 128));
-        k_fd_adjoint<<<ga, 128, lk.dl * sizeof(double), s>>>(lk, m->d, nb, Xc, m->ws.W.ptr, m->ws.Z.ptr, scale,
+        const size_t fd_smem = (size_t)(lk.dl + 3 * FD_TI) * sizeof(double);
+        if (fd_smem > 48 * 1024)
+          THY_CUDA_CHECK(cudaFuncSetAttribute(k_fd_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem));
+        k_fd_adjoint<<<ga, 128, fd_smem, s>>>(lk, m->d, nb, Xc, m->ws.W.ptr, m->ws.Z.ptr, scale,
                                                             grad + c0 * m->d, m->opt_fd_incremental);
       } else {
         dim3 ga((unsigned)ceil_div(lk.dl, GT), (unsigned)ceil_div(nb, GT));

@@ -64,6 +64,7 @@ struct LikDev {
 struct LikDevOwner {
   LikDev view{};
   DevBuf<double> A, off;
+  DevBuf<double> AF, AG;    // wide path: A re-tiled for the forward / adjoint DMMA GEMMs (built lazily)
   DevBuf<double2> yiv, yiv_lin;
   DevBuf<int> col;
   std::vector<int> col_host;
@@ -75,6 +76,7 @@ struct Workspace {  // grow-only scratch owned by the model, reused across evalu
   DevBuf<double> W;                     // generic path: weighted residuals [B][n_pad]
   DevBuf<double> partG, partL;          // stream-K partial tiles
   DevBuf<double> Z;                     // generic path scratch
+  DevBuf<double> XT;                    // wide path: packed / tiled chain vectors
   DevBuf<unsigned int> ticket;          // streaming kernel: last-CTA ticket, zero between launches
 };
 
