@@ -54,6 +54,21 @@ thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* lo
   return THY_OK;
 }
 
+static thy_status ensure_copy_streams(thy_model_s* m) {
+  if (m->h2d_stream) return THY_OK;
+  THY_CUDA_CHECK(cudaStreamCreateWithFlags(&m->h2d_stream, cudaStreamNonBlocking));
+  THY_CUDA_CHECK(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
+  THY_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) {
+    THY_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+    THY_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+  }
+  return THY_OK;
+}
+
+// Host-buffer entry point.  Large batches are cut into up to 4 chunks: the H2D copy of chunk k+1 and the D2H copy of
+// chunk k-1 run on their own streams while the kernels of chunk k execute (pinned host buffers make the copies truly
+// asynchronous; pageable buffers still work, just without overlap).
 static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad) {
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   THY_TRY(require_device());
@@ -65,10 +80,43 @@ static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* o
   THY_TRY(m->ws.logp.reserve((size_t)B));
   if (out_grad) THY_TRY(m->ws.grad.reserve(nx));
   cudaStream_t s = m->stream;
-  THY_CUDA_CHECK(cudaMemcpyAsync(m->ws.X.ptr, X, nx * sizeof(double), cudaMemcpyHostToDevice, s));
-  THY_TRY(eval_batch_dev(m, B, m->ws.X.ptr, m->ws.logp.ptr, out_grad ? m->ws.grad.ptr : nullptr, false));
-  THY_CUDA_CHECK(cudaMemcpyAsync(out_logp, m->ws.logp.ptr, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (out_grad) THY_CUDA_CHECK(cudaMemcpyAsync(out_grad, m->ws.grad.ptr, nx * sizeof(double), cudaMemcpyDeviceToHost, s));
+  static const int max_chunks = [] {   // THY_HOST_CHUNKS=1 disables the copy/compute overlap (diagnostics)
+    const char* e = std::getenv("THY_HOST_CHUNKS");
+    const int v = e ? std::atoi(e) : 2;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  int nch = (int)(B / 1024);
+  if (nch > max_chunks) nch = max_chunks;
+  if (nch < 2) {
+    THY_CUDA_CHECK(cudaMemcpyAsync(m->ws.X.ptr, X, nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    THY_TRY(eval_batch_dev(m, B, m->ws.X.ptr, m->ws.logp.ptr, out_grad ? m->ws.grad.ptr : nullptr, false));
+    THY_CUDA_CHECK(cudaMemcpyAsync(out_logp, m->ws.logp.ptr, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_grad) THY_CUDA_CHECK(cudaMemcpyAsync(out_grad, m->ws.grad.ptr, nx * sizeof(double), cudaMemcpyDeviceToHost, s));
+    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+    return THY_OK;
+  }
+  THY_TRY(ensure_copy_streams(m));
+  const int64_t per = ((B + nch - 1) / nch + 63) / 64 * 64;   // whole 64-chain tiles per chunk
+  // the copy streams must not start before earlier work on the model's stream has finished with the staging buffers
+  THY_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(m->h2d_stream, m->ev_start, 0));
+  int k = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
+    const int64_t nb = (B - b0 < per) ? (B - b0) : per;
+    const size_t off = (size_t)b0 * m->d, cnt = (size_t)nb * m->d;
+    THY_CUDA_CHECK(cudaMemcpyAsync(m->ws.X.ptr + off, X + off, cnt * sizeof(double), cudaMemcpyHostToDevice, m->h2d_stream));
+    THY_CUDA_CHECK(cudaEventRecord(m->ev_h2d[k], m->h2d_stream));
+    THY_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_h2d[k], 0));
+    THY_TRY(eval_batch_dev(m, nb, m->ws.X.ptr + off, m->ws.logp.ptr + b0, out_grad ? m->ws.grad.ptr + off : nullptr, false));
+    THY_CUDA_CHECK(cudaEventRecord(m->ev_done[k], s));
+    THY_CUDA_CHECK(cudaStreamWaitEvent(m->d2h_stream, m->ev_done[k], 0));
+    THY_CUDA_CHECK(cudaMemcpyAsync(out_logp + b0, m->ws.logp.ptr + b0, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost,
+                                   m->d2h_stream));
+    if (out_grad)
+      THY_CUDA_CHECK(cudaMemcpyAsync(out_grad + off, m->ws.grad.ptr + off, cnt * sizeof(double), cudaMemcpyDeviceToHost,
+                                     m->d2h_stream));
+  }
+  THY_CUDA_CHECK(cudaStreamSynchronize(m->d2h_stream));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
   return THY_OK;
 }

@@ -18,8 +18,8 @@
 //     every fragment load of both GEMMs bank-conflict free;
 //   * GEMM2  G^T[8 x d] += W^T[8 x 8 obs] . A_blk     (K = 8 obs, two k4 steps);
 //   * persistent grid (one CTA per SM), stream-K split of the (chain tile, row block) space so every SM gets the same
-//     number of row blocks; tiles split across CTAs go through partial buffers and a deterministic finish kernel,
-//     tiles owned by one CTA are finished in-kernel.
+//     number of row blocks; tiles split across CTAs go through partial buffers and are combined, in CTA order, by
+//     the last warp to deliver its segment (atomic ticket per (tile, warp)): deterministic, and ONE launch per term.
 // Z = A X (n x B, 328 MB at the 100-d / 10k-obs / 4096-chain config) is never materialised.
 #include "kernels.h"
 #include "ptx.cuh"
@@ -44,6 +44,7 @@ struct FusedParams {
   double* grad;           // [B][d] or null
   double* partG;          // [2G][TILE_B][NP]
   double* partL;          // [2G][TILE_B]
+  unsigned int* tickets;  // [T][NW] segments of (tile, warp) finished so far; zero between launches
   long long B;
   int d, dl, n, nblk;     // nblk = n_pad / MB
   long long T, U;         // chain tiles, units
@@ -69,6 +70,68 @@ __device__ __forceinline__ double apply_logp(int distribution, double q, int n, 
 __device__ __forceinline__ double apply_scale(int distribution, double q, int n, double cauchy_sign) {
   if (distribution == THY_DIST_GAUSSIAN) return 1.0;
   return -cauchy_sign * (1.0 + n) / (1.0 + q);
+}
+
+// Stream-K combine.  The last warp to deliver its segment of a (tile, warp) row group sums all segments, always in CTA
+// order, so the result does not depend on which CTA happens to finish last (run-to-run bit-identical).  Kept out of
+// line: it runs at most twice per CTA and must not cost the main loop any registers.
+template <int NT, bool WANT_GRAD>
+__device__ __noinline__ void combine_segments(const FusedParams& p, long long tile, int warp, int lane, long long G) {
+  using C = Cfg<NT>;
+  const int g8 = lane >> 2, q4 = lane & 3;
+  const int row = warp * 8 + g8;
+  const long long chain = tile * TILE_B + row;
+  const long long tb = tile * p.nblk, te = tb + p.nblk;
+  long long c_lo = (tb * G) / p.U;
+  while (c_lo > 0 && unit_begin(c_lo, p.U, G) > tb) --c_lo;
+  while (unit_begin(c_lo + 1, p.U, G) <= tb) ++c_lo;
+  long long c_hi = ((te - 1) * G) / p.U;
+  while (c_hi > 0 && unit_begin(c_hi, p.U, G) > te - 1) --c_hi;
+  while (unit_begin(c_hi + 1, p.U, G) <= te - 1) ++c_hi;
+  unsigned int nseg = 0;
+  for (long long cc = c_lo; cc <= c_hi; ++cc) nseg += (unit_begin(cc, p.U, G) != unit_begin(cc + 1, p.U, G)) ? 1u : 0u;
+  __threadfence();
+  __syncwarp();
+  unsigned int prev = 0;
+  if (lane == 0) prev = atomicAdd(&p.tickets[tile * NW + warp], 1u);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev != nseg - 1) return;
+  __threadfence();
+  double qtot = 0.0;
+  double gs[WANT_GRAD ? NT : 1][2];
+  if (WANT_GRAD) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) gs[t][0] = gs[t][1] = 0.0;
+  }
+  for (long long cc = c_lo; cc <= c_hi; ++cc) {
+    const long long cb = unit_begin(cc, p.U, G);
+    if (cb == unit_begin(cc + 1, p.U, G)) continue;   // CTA without work wrote nothing
+    const long long sl = 2 * cc + ((cb >= tb) ? 0 : 1);
+    qtot += __ldcg(&p.partL[sl * TILE_B + row]);
+    if (WANT_GRAD) {
+      const double* prow = p.partG + ((size_t)sl * TILE_B + row) * C::NP;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(prow + 8 * t + 2 * q4));
+        gs[WANT_GRAD ? t : 0][0] += v.x;
+        gs[WANT_GRAD ? t : 0][1] += v.y;
+      }
+    }
+  }
+  if (chain < p.B) {
+    if (q4 == 0) p.logp[chain] += apply_logp(p.distribution, qtot, p.n, p.log_const);
+    if (WANT_GRAD) {
+      const double sc = apply_scale(p.distribution, qtot, p.n, p.cauchy_sign);
+      double* grow = p.grad + chain * p.d;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int j = 8 * t + 2 * q4;
+        if (j < p.dl) grow[p.col[j]] += sc * gs[WANT_GRAD ? t : 0][0];
+        if (j + 1 < p.dl) grow[p.col[j + 1]] += sc * gs[WANT_GRAD ? t : 0][1];
+      }
+    }
+  }
+  if (lane == 0) p.tickets[tile * NW + warp] = 0u;   // re-arm for the next launch
 }
 
 template <int NT, bool WANT_GRAD>
@@ -164,6 +227,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedPara
         for (int t = 0; t < NT; ++t)
           *reinterpret_cast<double2*>(prow + 8 * t + 2 * q4) = make_double2(ga[WANT_GRAD ? t : 0][0], ga[WANT_GRAD ? t : 0][1]);
       }
+      combine_segments<NT, WANT_GRAD>(p, tile, warp, lane, G);
     }
   };
 
@@ -242,45 +306,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedPara
   if (cur_tile >= 0) flush(cur_tile, seg_begin, u1);
 }
 
-// Finish: tiles split across several CTAs -- sum their partials in CTA order (deterministic) and apply.
-template <int NT>
-__global__ void __launch_bounds__(256) k_fused_finish(const FusedParams p, long long G) {
-  using C = Cfg<NT>;
-  const int lane = threadIdx.x & 31;
-  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= p.B) return;
-  const long long t = b / TILE_B;
-  const int row = (int)(b % TILE_B);
-  const long long ub = t * p.nblk, ue = ub + p.nblk;
-  // first CTA whose range contains unit ub, last CTA whose range contains unit ue-1
-  long long c_lo = (ub * G) / p.U;
-  while (c_lo > 0 && unit_begin(c_lo, p.U, G) > ub) --c_lo;
-  while (unit_begin(c_lo + 1, p.U, G) <= ub) ++c_lo;
-  long long c_hi = ((ue - 1) * G) / p.U;
-  while (c_hi > 0 && unit_begin(c_hi, p.U, G) > ue - 1) --c_hi;
-  while (unit_begin(c_hi + 1, p.U, G) <= ue - 1) ++c_hi;
-  if (c_lo == c_hi) return;  // whole tile owned by one CTA: finished in-kernel
-  double q = 0.0;
-  for (long long c = c_lo; c <= c_hi; ++c) {
-    if (unit_begin(c, p.U, G) == unit_begin(c + 1, p.U, G)) continue;  // CTA without work wrote nothing
-    const long long slot = 2 * c + ((unit_begin(c, p.U, G) >= ub) ? 0 : 1);
-    q += p.partL[slot * TILE_B + row];
-  }
-  if (lane == 0) p.logp[b] += apply_logp(p.distribution, q, p.n, p.log_const);
-  if (p.grad) {
-    const double sc = apply_scale(p.distribution, q, p.n, p.cauchy_sign);
-    for (int j = lane; j < p.dl; j += 32) {
-      double s = 0.0;
-      for (long long c = c_lo; c <= c_hi; ++c) {
-        if (unit_begin(c, p.U, G) == unit_begin(c + 1, p.U, G)) continue;
-        const long long slot = 2 * c + ((unit_begin(c, p.U, G) >= ub) ? 0 : 1);
-        s += p.partG[((size_t)slot * TILE_B + row) * C::NP + j];
-      }
-      p.grad[b * p.d + p.col[j]] += sc * s;
-    }
-  }
-}
-
 template <int NT>
 thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_t s) {
   using C = Cfg<NT>;
@@ -294,6 +319,12 @@ thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_
   THY_TRY(m->ws.partL.reserve((size_t)2 * G * TILE_B));
   p.partG = m->ws.partG.ptr;
   p.partL = m->ws.partL.ptr;
+  const size_t n_tickets = (size_t)p.T * NW;
+  if (m->ws.fused_tickets.count < n_tickets) {
+    THY_TRY(m->ws.fused_tickets.reserve(n_tickets));
+    THY_CUDA_CHECK(cudaMemsetAsync(m->ws.fused_tickets.ptr, 0, m->ws.fused_tickets.count * sizeof(unsigned int), s));
+  }
+  p.tickets = m->ws.fused_tickets.ptr;
   KernelTimer timer(m, s);
   if (want_grad) {
     THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -303,8 +334,7 @@ thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_
     k_fused_dmma<NT, false><<<G, (NW + 1) * 32, smem, s>>>(p);
   }
   timer.stop();
-  k_fused_finish<NT><<<(unsigned)ceil_div(p.B, 8), 256, 0, s>>>(p, G);
-  count_launch(2);
+  count_launch();
   THY_CUDA_CHECK(cudaGetLastError());
   return THY_OK;
 }

@@ -122,6 +122,15 @@ thy_status thy_model_create(thy_model_t* out) {
 }
 
 thy_status thy_model_destroy(thy_model_t m) {
+  if (m && m->h2d_stream) {
+    cudaStreamDestroy(m->h2d_stream);
+    cudaStreamDestroy(m->d2h_stream);
+    cudaEventDestroy(m->ev_start);
+    for (int i = 0; i < 8; ++i) {
+      cudaEventDestroy(m->ev_h2d[i]);
+      cudaEventDestroy(m->ev_done[i]);
+    }
+  }
   delete m;
   return THY_OK;
 }

@@ -78,6 +78,7 @@ struct Workspace {  // grow-only scratch owned by the model, reused across evalu
   DevBuf<double> Z;                     // generic path scratch
   DevBuf<double> XT;                    // wide path: packed / tiled chain vectors
   DevBuf<unsigned int> ticket;          // streaming kernel: last-CTA ticket, zero between launches
+  DevBuf<unsigned int> fused_tickets;   // fused kernel: per (tile, warp) segment tickets, zero between launches
 };
 
 }  // namespace thy
@@ -102,6 +103,9 @@ struct thy_model_s {
   std::vector<std::unique_ptr<thy::LikDevOwner>> lik_dev;
   thy::Workspace ws;
   const char* last_path = "none";
+  // host-pointer API: copy streams + events so the H2D / D2H copies of one chunk overlap the kernels of the next
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d[8] = {}, ev_done[8] = {}, ev_start = nullptr;
   // optional CUDA-event timing of the dominant kernel (bench.py's roofline leg)
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
