@@ -6,14 +6,16 @@
 
 namespace thy {
 
-thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign) {
+thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign,
+                          bool likelihoods_only) {
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (B < 0) return fail(THY_ERR_INVALID_ARGUMENT, "negative batch size");
   if (B == 0) return THY_OK;
   if (!X || !logp) return fail(THY_ERR_INVALID_ARGUMENT, "null device pointer");
   const double csign = (cauchy_correct_sign || !m->opt_cauchy_ref_sign) ? -1.0 : 1.0;
   cudaStream_t s = m->stream;
-  THY_TRY(launch_prior(m->prior_view, B, X, logp, grad, csign, s));
+  // likelihoods_only: logp (and grad) are already initialised by the caller; only the likelihood terms are added
+  if (!likelihoods_only) THY_TRY(launch_prior(m->prior_view, B, X, logp, grad, csign, s));
   for (auto& own : m->lik_dev) {
     const LikDev& lk = own->view;
     const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&

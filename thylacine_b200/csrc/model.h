@@ -137,7 +137,8 @@ struct KernelTimer {
   }
 };
 // eval.cu
-thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false);
+thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false,
+                          bool likelihoods_only = false);
 // sampling.cu
 thy_status sample_priors_dev(thy_model_s* m, int64_t B, uint64_t seed, double* X);
 }

@@ -35,7 +35,7 @@ struct thy_slq_s {
   thy::DevBuf<unsigned char> cub_tmp;
   thy::DevBuf<double> cand_all, cand_sorted;             // gathered candidates
   thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers
-  thy::DevBuf<int> slot;
+  thy::DevBuf<int> slot, accepted;
   thy::DevBuf<double> sigma, sig_part;                   // per-dimension spread of the live pool
   thy::DevBuf<double> scalars;                           // [0] walk scale, [1] threshold, [2] accepted, [3] proposed
   thy::DevBuf<int> count_dev;                            // [0] local retire count
@@ -56,11 +56,6 @@ namespace thy {
 __global__ void k_iota(int n, int* v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = i;
-}
-
-__global__ void k_sub(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = a[i] - b[i];
 }
 
 __global__ void k_fill(long long n, double* v, double val) {
@@ -113,18 +108,48 @@ __global__ void k_slq_threshold(const double* __restrict__ merged, int Kr, const
 // Per-dimension standard deviation of the live pool: deterministic two-stage reduction.
 __global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, int d, const double* __restrict__ x,
                                                         double* __restrict__ part, int nslab) {
-  // block = one slab of rows; threads stride over columns (coalesced), rows sequential
+  // block = one slab of rows, read as one contiguous stream (fully coalesced); thread t always sees the same column
+  // phase because the stride 256 * k is re-based per row group: element e of the slab has column (e0 + e) % d
+  __shared__ double ss[256], ss2[256];
   const int slab = blockIdx.x;
   const long long r0 = (Pl * slab) / nslab, r1 = (Pl * (slab + 1)) / nslab;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    double s = 0.0, s2 = 0.0;
-    for (long long r = r0; r < r1; ++r) {
-      const double v = x[r * d + j];
-      s += v;
-      s2 = fma(v, v, s2);
+  // rows handled in groups of RG rows so that RG * d is a multiple of 256-thread passes with a fixed column per thread
+  // (simple scheme: thread t owns column t % d of rows t / d, t / d + 256 / d, ... ; threads >= (256/d)*d idle)
+  const int rows_per_pass = 256 / d > 0 ? 256 / d : 1;
+  double s = 0.0, s2 = 0.0;
+  if (d <= 256) {
+    const int rr = threadIdx.x / d, j = threadIdx.x % d;
+    if (rr < rows_per_pass) {
+      for (long long r = r0 + rr; r < r1; r += rows_per_pass) {
+        const double v = x[r * d + j];
+        s += v;
+        s2 = fma(v, v, s2);
+      }
     }
-    part[((size_t)slab * 2 + 0) * d + j] = s;
-    part[((size_t)slab * 2 + 1) * d + j] = s2;
+    ss[threadIdx.x] = (rr < rows_per_pass) ? s : 0.0;
+    ss2[threadIdx.x] = (rr < rows_per_pass) ? s2 : 0.0;
+    __syncthreads();
+    if (threadIdx.x < d) {
+      double a = 0.0, a2 = 0.0;
+      for (int q = 0; q < rows_per_pass; ++q) {   // fixed order: deterministic
+        a += ss[q * d + threadIdx.x];
+        a2 += ss2[q * d + threadIdx.x];
+      }
+      part[((size_t)slab * 2 + 0) * d + threadIdx.x] = a;
+      part[((size_t)slab * 2 + 1) * d + threadIdx.x] = a2;
+    }
+  } else {
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+      s = 0.0;
+      s2 = 0.0;
+      for (long long r = r0; r < r1; ++r) {
+        const double v = x[r * d + j];
+        s += v;
+        s2 = fma(v, v, s2);
+      }
+      part[((size_t)slab * 2 + 0) * d + j] = s;
+      part[((size_t)slab * 2 + 1) * d + j] = s2;
+    }
   }
 }
 __global__ void k_slq_sigma_final(long long Pl, int d, const double* __restrict__ part, int nslab, double* __restrict__ sigma) {
@@ -175,12 +200,13 @@ __global__ void __launch_bounds__(256) k_slq_propose(int c, int d, uint64_t seed
 __global__ void __launch_bounds__(256) k_slq_accept(int c, int d, uint64_t seed, uint64_t step, int rank,
                                                     double* __restrict__ Y, double* __restrict__ yl, double* __restrict__ ypr,
                                                     const double* __restrict__ Yp, const double* __restrict__ tl,
-                                                    const double* __restrict__ tpr, double* __restrict__ scalars) {
+                                                    const double* __restrict__ tpr, const double* __restrict__ scalars,
+                                                    int* __restrict__ accepted) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= c) return;
   const double lprior_new = tpr[w];
-  const double lnew = tl[w] - lprior_new;
+  const double lnew = tl[w];
   const RngDraw u = rng_uniform2(seed, ((uint64_t)rank << 40) | (uint64_t)w, 0, RNG_SLQ_ACCEPT, step);
   const bool ok = isfinite(lprior_new) && isfinite(lnew) && (lnew > scalars[1]) &&
                   (lprior_new - ypr[w] >= log(1.0 - u.u0));
@@ -191,9 +217,8 @@ __global__ void __launch_bounds__(256) k_slq_accept(int c, int d, uint64_t seed,
     if (ok) {
       yl[w] = lnew;
       ypr[w] = lprior_new;
-      atomicAdd(&scalars[2], 1.0);   // integer-valued counts: exact and order-independent in fp64
+      accepted[w] += 1;   // per-walker tally, summed once per round by k_slq_adapt (no atomics)
     }
-    atomicAdd(&scalars[3], 1.0);
   }
 }
 
@@ -213,17 +238,29 @@ __global__ void __launch_bounds__(256) k_slq_commit(int c, int d, const int* __r
 
 // scale *= (1 + inc) when the round's acceptance beat the target, else /= (1 + inc)   (SlqConfig.domainScalingIncrement,
 // targetAcceptanceProbability play the same role for the reference's cube scaling, QuadratureDomainTelemetry.scala)
-__global__ void k_slq_adapt(double* scalars, double inc, double target) {
-  if (scalars[3] > 0.0) {
-    const double rate = scalars[2] / scalars[3];
+__global__ void __launch_bounds__(1024) k_slq_adapt(double* scalars, double inc, double target, int c, int steps,
+                                                    int* __restrict__ accepted) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int w = threadIdx.x; w < c; w += blockDim.x) {
+    a += (double)accepted[w];
+    accepted[w] = 0;
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double acc = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) acc += sh[i];
+  const double prop = (double)c * (double)steps;
+  if (prop > 0.0) {
+    const double rate = acc / prop;
     scalars[4] = rate;
     if (rate > target) scalars[0] *= (1.0 + inc); else scalars[0] /= (1.0 + inc);
     scalars[0] = fmin(fmax(scalars[0], 1e-6), 10.0);
   }
-  scalars[5] += scalars[2];
-  scalars[6] += scalars[3];
-  scalars[2] = 0.0;
-  scalars[3] = 0.0;
+  scalars[5] += acc;
+  scalars[6] += prop;
 }
 
 // Copy retired points (local sorted order == global order when world == 1).
@@ -260,46 +297,54 @@ __device__ __forceinline__ double log_half_gap(double lx_hi, double lx_lo) {
   return log(0.5) + lx_hi + log(-expm1(lx_lo - lx_hi));
 }
 
-__global__ void __launch_bounds__(256) k_slq_evidence(int Kr, long long n0, long long it0, uint64_t seed,
+constexpr int EVT = 1024;  // threads of the evidence kernel
+
+__global__ void __launch_bounds__(EVT) k_slq_evidence(int Kr, long long n0, long long it0, uint64_t seed,
                                                       const double* __restrict__ r, double* __restrict__ tmp_logx,
                                                       long long tmp_stride, double* __restrict__ state, int finalize,
                                                       double* __restrict__ out) {
-  __shared__ double sh[256];
+  __shared__ double wsum[EVT / 32];
   __shared__ double carry;
-  __shared__ double red_m[256], red_s[256], red_sl[256];
+  __shared__ double red_m[EVT], red_s[EVT], red_sl[EVT];
   const int a = blockIdx.x;
   double* st = state + (size_t)a * 8;
   double* lx = tmp_logx + (size_t)a * tmp_stride;
-  const int tid = threadIdx.x;
-  if (tid == 0) carry = st[0];
-  __syncthreads();
-  // pass 1: logX_j = logX_cur + sum_{k<j} ln t_k   (exclusive scan in chunks of 256)
-  for (int base = 0; base < Kr; base += 256) {
-    const int j = base + tid;
-    double lt = 0.0;
-    if (j < Kr) {
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  // pass 1: logX_j = logX_cur + sum_{k<j} ln t_k.  Each thread owns a contiguous segment: serial sum, block scan of
+  // the segment totals (warp shuffles), serial write-back.
+  {
+    const int S = (Kr + EVT - 1) / EVT;
+    const int j0 = tid * S < Kr ? tid * S : Kr, j1 = (j0 + S < Kr) ? j0 + S : Kr;
+    double local = 0.0;
+    for (int j = j0; j < j1; ++j) {
       const RngDraw u = rng_uniform2(seed, (uint64_t)a, 0, RNG_SLQ_SHRINK, (uint64_t)(it0 + j));
-      lt = log(1.0 - u.u0) / (double)(n0 - j);   // ln u^{1/n}, u in (0,1]
+      const double lt = log(1.0 - u.u0) / (double)(n0 - j);   // ln u^{1/n}, u in (0,1]
+      lx[j] = lt;
+      local += lt;
     }
-    sh[tid] = lt;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {  // inclusive Hillis-Steele scan
-      double v = (tid >= o) ? sh[tid - o] : 0.0;
-      __syncthreads();
-      sh[tid] += v;
-      __syncthreads();
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    const double incl = sh[tid];
-    const double c0 = carry;
-    if (j < Kr) lx[j] = c0 + incl - lt;
+    if (lane == 31) wsum[wrp] = incl;
     __syncthreads();
-    if (tid == 255) carry = c0 + incl;
+    double base = st[0];
+    for (int w = 0; w < wrp; ++w) base += wsum[w];
+    double run = base + (incl - local);
+    for (int j = j0; j < j1; ++j) {
+      const double lt = lx[j];
+      lx[j] = run;
+      run += lt;
+    }
+    if (tid == EVT - 1) carry = run;   // logX assigned to the first point of the next round
     __syncthreads();
   }
   // pass 2: finalise point j-1 once X_j is known: w_{j-1} = 1/2 (X_{j-2} - X_j)  (first ever point: 1/2 (X_0 - X_1))
   double m = -INFINITY, s = 0.0, sl = 0.0;
   const double pend = st[4];
-  for (int j = tid; j < Kr; j += 256) {
+  for (int j = tid; j < Kr; j += EVT) {
     double l_prev, lx_m2;
     bool have_prev = true, first_ever = false;
     if (j == 0) {
@@ -323,7 +368,7 @@ __global__ void __launch_bounds__(256) k_slq_evidence(int Kr, long long n0, long
   }
   red_m[tid] = m; red_s[tid] = s; red_sl[tid] = sl;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = EVT / 2; o > 0; o >>= 1) {
     if (tid < o) {
       double m2 = red_m[tid + o], s2 = red_s[tid + o], sl2 = red_sl[tid + o];
       double m1 = red_m[tid], s1 = red_s[tid], sl1 = red_sl[tid];
@@ -385,11 +430,13 @@ static thy_status slq_sort_keys(thy_slq_s* h, const double* in, double* out, int
   return THY_OK;
 }
 
-// log-likelihood = total log-posterior - log-prior for a batch
-static thy_status slq_eval(thy_slq_s* h, long long n, const double* X, double* total, double* prior) {
+// log-prior and log-likelihood of a batch, each evaluated once: the prior kernel writes `prior`, the likelihood terms
+// are accumulated into a zeroed `loglik` (no total - prior subtraction, so no cancellation either)
+static thy_status slq_eval(thy_slq_s* h, long long n, const double* X, double* loglik, double* prior) {
   thy_model_s* m = h->model;
   THY_TRY(launch_prior(m->prior_view, n, X, prior, nullptr, -1.0, m->stream));
-  THY_TRY(eval_batch_dev(m, n, X, total, nullptr, true));
+  THY_CUDA_CHECK(cudaMemsetAsync(loglik, 0, (size_t)n * sizeof(double), m->stream));
+  THY_TRY(eval_batch_dev(m, n, X, loglik, nullptr, true, true));
   h->evals += n;
   return THY_OK;
 }
@@ -397,7 +444,7 @@ static thy_status slq_eval(thy_slq_s* h, long long n, const double* X, double* t
 static thy_status slq_evidence(thy_slq_s* h, const double* retired_sorted, int Kr, long long n0, int finalize) {
   cudaStream_t s = h->model->stream;
   const long long stride = std::max<long long>(h->K, h->P);
-  k_slq_evidence<<<h->A, 256, 0, s>>>(Kr, n0, h->iterations, h->seed, retired_sorted, h->tmp_logx.ptr, stride,
+  k_slq_evidence<<<h->A, EVT, 0, s>>>(Kr, n0, h->iterations, h->seed, retired_sorted, h->tmp_logx.ptr, stride,
                                       h->abs_state.ptr, finalize, h->abs_out.ptr);
   count_launch();
   THY_CUDA_CHECK(cudaGetLastError());
@@ -434,7 +481,7 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
   }
   if (c > 0) {
     // per-dimension spread of the live pool sets the walk's proposal shape
-    const int nslab = 128;
+    const int nslab = 1184;   // 8 slabs per SM
     k_slq_sigma_part<<<nslab, 256, 0, s>>>(h->Pl, d, h->x.ptr, h->sig_part.ptr, nslab);
     k_slq_sigma_final<<<(unsigned)ceil_div(d, 128), 128, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
     k_slq_spawn<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, h->Pl, d, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr,
@@ -447,12 +494,13 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
                                                                                h->sigma.ptr, h->scalars.ptr, h->Yp.ptr);
       THY_TRY(slq_eval(h, c, h->Yp.ptr, h->tl.ptr, h->tpr.ptr));
       k_slq_accept<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
-                                                           h->Yp.ptr, h->tl.ptr, h->tpr.ptr, h->scalars.ptr);
+                                                           h->Yp.ptr, h->tl.ptr, h->tpr.ptr, h->scalars.ptr, h->accepted.ptr);
       count_launch(2);
     }
     k_slq_commit<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->slot.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr, h->x.ptr,
                                                          h->ll.ptr, h->lpr.ptr);
-    k_slq_adapt<<<1, 1, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability);
+    k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability, c, h->M,
+                                   h->accepted.ptr);
     count_launch(2);
   }
   THY_CUDA_CHECK(cudaGetLastError());
@@ -508,8 +556,8 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   chk(h->cand_all.reserve((size_t)std::max<long long>((long long)K * world, h->P)));
   chk(h->cand_sorted.reserve((size_t)std::max<long long>((long long)K * world, h->P)));
   chk(h->Y.reserve((size_t)K * d)); chk(h->Yp.reserve((size_t)K * d)); chk(h->yl.reserve(K)); chk(h->ypr.reserve(K));
-  chk(h->tl.reserve(K)); chk(h->tpr.reserve(K)); chk(h->slot.reserve(K));
-  chk(h->sigma.reserve(d)); chk(h->sig_part.reserve((size_t)128 * 2 * d));
+  chk(h->tl.reserve(K)); chk(h->tpr.reserve(K)); chk(h->slot.reserve(K)); chk(h->accepted.reserve(K));
+  chk(h->sigma.reserve(d)); chk(h->sig_part.reserve((size_t)1184 * 2 * d));
   chk(h->scalars.reserve(8)); chk(h->count_dev.reserve(1));
   chk(h->tmp_logx.reserve((size_t)h->A * std::max<long long>(K, h->P)));
   chk(h->abs_state.reserve((size_t)h->A * 8)); chk(h->abs_out.reserve((size_t)h->A * 2));
@@ -530,14 +578,15 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   }
   if (st == THY_OK) {
     chk(slq_eval(h, Pl, h->x.ptr, h->ll.ptr, h->lpr.ptr));
-    k_sub<<<(unsigned)ceil_div(Pl, 256), 256, 0, s>>>(Pl, h->ll.ptr, h->lpr.ptr, h->ll.ptr);
     k_iota<<<(unsigned)ceil_div(Pl, 256), 256, 0, s>>>((int)Pl, h->idx_in.ptr);
     std::vector<double> sc = {0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (st == THY_OK && cudaMemsetAsync(h->accepted.ptr, 0, (size_t)K * sizeof(int), s) != cudaSuccess)
+      st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
     chk(h->scalars.upload(sc, s));
     std::vector<double> stt((size_t)h->A * 8, 0.0);
     for (int a = 0; a < h->A; ++a) stt[(size_t)a * 8 + 5] = -INFINITY;
     chk(h->abs_state.upload(stt, s));
-    count_launch(2);
+    count_launch();
     if (cudaStreamSynchronize(s) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
   }
   if (st != THY_OK) {
