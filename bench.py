@@ -89,6 +89,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs are meant to use every host thread."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import ThreadpoolController
+        global _THREADPOOL
+        _THREADPOOL = ThreadpoolController()
+        _THREADPOOL.limit(limits=cores)       # stays in force for the life of the process
+    except Exception:
+        pass
+    return cores
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def literal_reference_evals(prob, points, budget_s):
     """The reference's algorithm executed literally (oracle port): dense n x n covariance, LU solve per logPdf
@@ -127,7 +140,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = use_all_host_cores()
     prob = synthetic_problem()
     pts = chain_points(prob, args.steps + args.warmup, seed=7)
     # warm-up builds the lazily cached Cholesky / inverse exactly as the reference's lazy vals would
@@ -302,7 +315,7 @@ def run_ours(args):
                 traffic = None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = use_all_host_cores()
             v, evals = structured_port_evals_per_s(prob, chain_points(prob, CHAINS, seed=9), 10.0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{evals} evals of the same C2 model in batches of {CHAINS}: oracle/ref_oracle.linear_gaussian_batch "
