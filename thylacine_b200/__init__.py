@@ -14,3 +14,8 @@ from .samplers import HmcmcConfig, HmcmcSampledPosterior, HmcmcTelemetryUpdate  
 from .samplers import LeapfrogMcmcConfig, LeapfrogMcmcSampledPosterior  # noqa: F401,E402
 from .samplers import SampleMoments, SlqConfig, SlqIntegratedPosterior, SlqTelemetryUpdate  # noqa: F401,E402
 from .distributed import Communicator, shard_range  # noqa: F401,E402
+from .optimisers import (  # noqa: F401,E402
+    ConjugateGradientConfig, ConjugateGradientOptimisedPosterior, CoordinateSlideConfig, CoordinateSlideOptimisedPosterior,
+    HookeAndJeevesConfig, HookeAndJeevesOptimisedPosterior, MdsConfig, MdsOptimisedPosterior, OptimisationTelemetryUpdate,
+)
+from .analytic import GaussianAnalyticPosterior  # noqa: F401,E402
