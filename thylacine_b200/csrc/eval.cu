@@ -6,6 +6,47 @@
 
 namespace thy {
 
+// One likelihood term added into logp / grad: kernel-path selection lives here.
+thy_status launch_likelihood(thy_model_s* m, LikDevOwner& owner, int64_t B, const double* X, double* logp, double* grad,
+                             double csign, cudaStream_t s) {
+  LikDevOwner* own = &owner;
+  const LikDev& lk = own->view;
+  const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&
+                       lk.distribution != THY_DIST_UNIFORM);
+  int path = m->opt_kernel_path;
+  if (path == 2 && !(linear && fused_dmma_supported(lk, grad != nullptr)))
+    return fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
+  if (path == 3 && !(linear && stream_supported(lk, B)))
+    return fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
+  if (path == 4 && !wide_supported(lk))
+    return fail(THY_ERR_UNSUPPORTED, "wide DMMA path does not support this likelihood (uniform observations / FD Jacobian)");
+  if (path == 0) {
+    if (linear && stream_supported(lk, B) &&
+        (!fused_dmma_supported(lk, grad != nullptr) || stream_cost_model(lk, B) <= fused_cost_model(lk, B)))
+      path = 3;
+    else if (linear && fused_dmma_supported(lk, grad != nullptr))
+      path = 2;
+    else if (wide_supported(lk) && B >= 32 && (long long)lk.n * lk.dl >= 4096)
+      path = 4;
+    else
+      path = 1;
+  }
+  if (path == 2) {
+    m->last_path = "fused_dmma";
+    THY_TRY(launch_fused_dmma(m, *own, B, X, logp, grad, csign, s));
+  } else if (path == 3) {
+    m->last_path = "stream";
+    THY_TRY(launch_stream(m, *own, B, X, logp, grad, csign, s));
+  } else if (path == 4) {
+    m->last_path = "wide_dmma";
+    THY_TRY(launch_wide_likelihood(m, *own, B, X, logp, grad, csign, s));
+  } else {
+    m->last_path = "generic";
+    THY_TRY(launch_generic_likelihood(m, *own, B, X, logp, grad, csign, s));
+  }
+  return THY_OK;
+}
+
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign,
                           bool likelihoods_only) {
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
@@ -16,42 +57,7 @@ thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* lo
   cudaStream_t s = m->stream;
   // likelihoods_only: logp (and grad) are already initialised by the caller; only the likelihood terms are added
   if (!likelihoods_only) THY_TRY(launch_prior(m->prior_view, B, X, logp, grad, csign, s));
-  for (auto& own : m->lik_dev) {
-    const LikDev& lk = own->view;
-    const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&
-                         lk.distribution != THY_DIST_UNIFORM);
-    int path = m->opt_kernel_path;
-    if (path == 2 && !(linear && fused_dmma_supported(lk, grad != nullptr)))
-      return fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
-    if (path == 3 && !(linear && stream_supported(lk, B)))
-      return fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
-    if (path == 4 && !wide_supported(lk))
-      return fail(THY_ERR_UNSUPPORTED, "wide DMMA path does not support this likelihood (uniform observations / FD Jacobian)");
-    if (path == 0) {
-      if (linear && stream_supported(lk, B) &&
-          (!fused_dmma_supported(lk, grad != nullptr) || stream_cost_model(lk, B) <= fused_cost_model(lk, B)))
-        path = 3;
-      else if (linear && fused_dmma_supported(lk, grad != nullptr))
-        path = 2;
-      else if (wide_supported(lk) && B >= 32 && (long long)lk.n * lk.dl >= 4096)
-        path = 4;
-      else
-        path = 1;
-    }
-    if (path == 2) {
-      m->last_path = "fused_dmma";
-      THY_TRY(launch_fused_dmma(m, *own, B, X, logp, grad, csign, s));
-    } else if (path == 3) {
-      m->last_path = "stream";
-      THY_TRY(launch_stream(m, *own, B, X, logp, grad, csign, s));
-    } else if (path == 4) {
-      m->last_path = "wide_dmma";
-      THY_TRY(launch_wide_likelihood(m, *own, B, X, logp, grad, csign, s));
-    } else {
-      m->last_path = "generic";
-      THY_TRY(launch_generic_likelihood(m, *own, B, X, logp, grad, csign, s));
-    }
-  }
+  for (auto& own : m->lik_dev) THY_TRY(launch_likelihood(m, *own, B, X, logp, grad, csign, s));
   if (m->lik_dev.empty()) m->last_path = "priors_only";
   return THY_OK;
 }
