@@ -127,6 +127,19 @@ thy_status thy_model_set_option(thy_model_t m, int option, int value);
 /* Sorts labels ascending (posterior/Posterior.scala:40-48, core/GenericIdentifier.scala:29-30), builds the flat
  * layout, validates every likelihood label against the priors, uploads constants to the current device.   */
 thy_status thy_model_finalize(thy_model_t m);
+/* Gaussian collapse (SURVEY.md 8(d) reduced-flop form).  Builds a NEW finalized model with the same priors and label
+ * layout in which all GaussianLinearLikelihood terms (likelihood/GaussianLinearLikelihood.scala:62-83) are replaced by
+ * ONE d'-observation linear-Gaussian term (A' = L^T, L L^T = sum A^T Sigma^-1 A computed on the device) that has the
+ * same log-density and gradient at every point: 4 d'^2 instead of 4 n d flops per evaluation.  Every engine runs on
+ * the collapsed model unchanged.  THY_ERR_UNSUPPORTED for non-Gaussian / non-linear terms or a singular Gram matrix.
+ * The caller owns *out (thy_model_destroy). */
+thy_status thy_model_collapse(thy_model_t m, thy_model_t* out);
+/* GaussianAnalyticPosterior (components/posterior/GaussianAnalyticPosterior.scala:141-169: rawDistribution; :72-79
+ * mean / covariance / maxLogPdf): Lambda = Sigma_p^-1 + A^T Sigma_d^-1 A on the device, Cholesky on the host.
+ * Gaussian priors and GaussianLinearLikelihoods only.  Any output may be NULL.  out_log_evidence = ln of the integral
+ * of the unnormalised posterior (the analytic evidence the SLQ tests compare against). */
+thy_status thy_model_gaussian_posterior(thy_model_t m, double* out_mean, double* out_covariance, double* out_precision,
+                                        double* out_log_evidence, double* out_max_logpdf);
 /* domainDimension (Posterior.scala:37-38) */
 thy_status thy_model_dimension(thy_model_t m, int* out_dim);
 /* offset and width of a label inside the flat vector (ModelParameterContext.scala:42-80) */

@@ -78,6 +78,8 @@ SIGNATURES = {
     "thy_model_last_kernel_path": (C.c_char_p, [_vp]),
     "thy_model_enable_timing": (C.c_int, [_vp, C.c_int]),
     "thy_model_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "thy_model_collapse": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "thy_model_gaussian_posterior": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "thy_sample_priors": (C.c_int, [_vp, C.c_int64, C.c_uint64, _dp]),
     "thy_sample_priors_dev": (C.c_int, [_vp, C.c_int64, C.c_uint64, _vp]),
 }

@@ -3,11 +3,12 @@
 Reference: /root/reference/src/main/scala/thylacine/model/components/posterior/GaussianAnalyticPosterior.scala
     :141-169  Lambda = Sigma_p^-1 + A^T Sigma_d^-1 A,  mean = Lambda^-1 (Sigma_p^-1 mu_p + A^T Sigma_d^-1 y)
     :72-116   maxLogPdf, entropy, mean, covarianceStridedVector, logPdfAt, sample, init
-For Gaussian priors and linear-Gaussian likelihoods the log-posterior gradient is exactly affine,
-grad(x) = b - Lambda x, so ONE batched device evaluation at the d + 1 points {0, e_1, ..., e_d} yields b and every
-column of Lambda (the forward and adjoint passes over A do the A^T Sigma^-1 A work on the tensor cores); the d x d
-Cholesky factorisation stays on the host.  The reference concatenates prior blocks in Set iteration order while its
-transform columns use sorted order (latent bug); here everything is in label-sorted order.
+The precision Lambda and the information vector are assembled by the C library (``thy_model_gaussian_posterior``,
+csrc/collapse.cu): the likelihood part A^T Sigma_d^-1 A comes from the device's own forward + adjoint kernels applied to
+the homogeneous problem at the unit vectors (no cancellation against the information vector), the prior part and the
+d x d Cholesky factorisation are host-side one-offs inside the library.  The reference concatenates prior blocks in Set
+iteration order while its transform columns use sorted order (latent bug); here everything is in
+label-sorted order.
 """
 from __future__ import annotations
 
@@ -33,18 +34,8 @@ class GaussianAnalyticPosterior:
 
     def init(self) -> None:
         """Builds the posterior distribution (the reference's ``init`` forces its lazy ``rawDistribution``, :116-119)."""
-        d = self.posterior.domainDimension
-        X = np.zeros((d + 1, d))
-        X[np.arange(1, d + 1), np.arange(d)] = 1.0
-        _, g = self.posterior.logPdfGradBatch(X)
-        b = g[0]
-        lam = (b[None, :] - g[1:]).T                    # column j of Lambda = grad(0) - grad(e_j)
-        lam = 0.5 * (lam + lam.T)
+        self._mean, self._cov, lam, self._log_evidence, self._max_logpdf = self.posterior.gaussianPosterior()
         self._chol = np.linalg.cholesky(lam)
-        y = np.linalg.solve(self._chol, b)
-        self._mean = np.linalg.solve(self._chol.T, y)
-        eye = np.eye(d)
-        self._cov = np.linalg.solve(self._chol.T, np.linalg.solve(self._chol, eye))
         self._precision = lam
         self._ready = True
 
@@ -89,7 +80,14 @@ class GaussianAnalyticPosterior:
 
     @property
     def maxLogPdf(self) -> float:
-        return self.logPdfAt(self.posterior.unflatten(self.meanVector))
+        self._need()
+        return self._max_logpdf
+
+    @property
+    def logEvidence(self) -> float:
+        """ln of the integral of the unnormalised posterior (not in the reference; the yardstick of the SLQ tests)."""
+        self._need()
+        return self._log_evidence
 
     def sampleArray(self, numberOfSamples: int, rngSeed: int = 0) -> np.ndarray:
         self._need()

@@ -260,6 +260,27 @@ class UnnormalisedPosterior:
         desc.differential = fm.differential
         check(self._lib.thy_model_add_likelihood(self._h, C.byref(desc)))
 
+    def collapsed(self) -> "UnnormalisedPosterior":
+        """The same posterior with every GaussianLinearLikelihood term folded into ONE d-observation linear-Gaussian
+        term (``thy_model_collapse``; SURVEY.md 8(d) reduced-flop form): identical log-density and gradient at every
+        point for 4 d^2 instead of 4 n d flops per evaluation.  Priors (of any kind) and the label layout are kept, so
+        the samplers and the SLQ engine take the collapsed posterior unchanged."""
+        h = C.c_void_p()
+        check(self._lib.thy_model_collapse(self._h, C.byref(h)))
+        other = object.__new__(UnnormalisedPosterior)
+        other._lib, other._h = self._lib, h
+        other.domainDimension, other.layout = self.domainDimension, dict(self.layout)
+        return other
+
+    def gaussianPosterior(self):
+        """(mean, covariance, precision, log_evidence, max_logpdf) of the analytic Gaussian posterior
+        (``thy_model_gaussian_posterior``; GaussianAnalyticPosterior.scala:141-169)."""
+        d = self.domainDimension
+        mean, cov, prec = np.empty(d), np.empty((d, d)), np.empty((d, d))
+        lz, mx = C.c_double(), C.c_double()
+        check(self._lib.thy_model_gaussian_posterior(self._h, _ptr(mean), _ptr(cov), _ptr(prec), C.byref(lz), C.byref(mx)))
+        return mean, cov, prec, lz.value, mx.value
+
     # -- lifetime
     def close(self) -> None:
         if getattr(self, "_h", None):

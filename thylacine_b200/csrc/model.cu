@@ -43,7 +43,7 @@ int sm_count() {
 }
 
 // Lower Cholesky factor of a dense SPD matrix (row-major), in place into L; false if not SPD.
-static bool cholesky_lower(const std::vector<double>& S, int n, std::vector<double>& L) {
+bool cholesky_lower(const std::vector<double>& S, int n, std::vector<double>& L) {
   L.assign((size_t)n * n, 0.0);
   for (int i = 0; i < n; ++i) {
     for (int j = 0; j <= i; ++j) {
@@ -61,7 +61,7 @@ static bool cholesky_lower(const std::vector<double>& S, int n, std::vector<doub
 }
 
 // Inverse of an SPD matrix from its Cholesky factor (long-double accumulation).
-static void spd_inverse(const std::vector<double>& L, int n, std::vector<double>& P) {
+void spd_inverse(const std::vector<double>& L, int n, std::vector<double>& P) {
   std::vector<long double> Li((size_t)n * n, 0.0L);  // inverse of L (lower)
   for (int i = 0; i < n; ++i) {
     Li[(size_t)i * n + i] = 1.0L / L[(size_t)i * n + i];
@@ -101,6 +101,88 @@ static thy_status ci_to_var(const double* ci, int n, std::vector<double>& var) {
     if (!(ci[i] > 0)) return fail(THY_ERR_INVALID_ARGUMENT, "confidence intervals must be > 0 (RecordedData.scala:57)");
     var[i] = std::pow(ci[i] / 2, 2);  // Math.pow(ci / 2, 2)
   }
+  return THY_OK;
+}
+
+}  // namespace thy
+
+namespace thy {
+
+// Uploads one likelihood term: the column blocks (ascending label order, already resolved to flat columns `cols`)
+// are merged into the padded coefficient matrix, observations into (y, 1/var) pairs.  `log_const_override` replaces
+// the distribution's own normaliser (used by the collapsed Gaussian term, collapse.cu).
+thy_status build_lik_dev(thy_model_s* m, int distribution, int link, int jacobian, double differential, int n,
+                         const std::vector<int>& cols, const std::vector<const double*>& blocks,
+                         const std::vector<int>& widths, const double* meas, const double* unc, const double* offset,
+                         const double* log_const_override) {
+  const double LOG_2PI = std::log(2.0 * M_PI);
+  auto own = std::make_unique<LikDevOwner>();
+  const int dl = (int)cols.size();
+  const int n_pad = (int)round_up(n, 32);
+  // row pitch = 4 (mod 8) doubles: conflict-free DMMA fragment loads (kernels_fused_dmma.cu)
+  const int nt = fused_nt_for(dl);
+  const int lds = (nt > 0 ? 8 * nt : (int)round_up(dl, 8)) + 4;
+  std::vector<double> A((size_t)n_pad * lds, 0.0);
+  own->col_host = cols;
+  int c0 = 0;
+  for (size_t b = 0; b < blocks.size(); ++b) {
+    const int w = widths[b];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < w; ++j) A[(size_t)i * lds + c0 + j] = blocks[b][(size_t)i * w + j];
+    c0 += w;
+  }
+  own->contiguous = true;
+  for (int k = 1; k < dl; ++k)
+    if (own->col_host[k] != own->col_host[0] + k) own->contiguous = false;
+  std::vector<double2> yiv(n_pad, make_double2(0.0, 0.0)), yiv_lin(n_pad, make_double2(0.0, 0.0));
+  std::vector<double> offv(n_pad, 0.0);
+  double lc = 0.0;
+  if (distribution == THY_DIST_UNIFORM) {
+    for (int i = 0; i < n; ++i) {
+      yiv[i] = make_double2(meas[i], unc[i]);  // (upper, lower)
+      lc -= std::log(meas[i] - unc[i]);
+    }
+    // padded rows must always pass the bounds test on f = 0
+    for (int i = n; i < n_pad; ++i) yiv[i] = make_double2(1.0, -1.0);
+  } else {
+    double logdet = 0.0, lognorm = n / 2.0 * LOG_2PI;
+    for (int i = 0; i < n; ++i) {
+      const double o = offset ? offset[i] : 0.0;
+      yiv[i] = make_double2(meas[i], 1.0 / unc[i]);
+      yiv_lin[i] = make_double2(meas[i] - o, 1.0 / unc[i]);
+      logdet += std::log(unc[i]);
+      lognorm += std::log(std::sqrt(unc[i]));
+    }
+    if (distribution == THY_DIST_GAUSSIAN)
+      lc = -lognorm;
+    else
+      lc = std::lgamma((1 + n) / 2.0) - std::lgamma(0.5) - n / 2.0 * std::log(M_PI) - logdet / 2.0;
+  }
+  if (log_const_override) lc = *log_const_override;
+  if (offset)
+    for (int i = 0; i < n; ++i) offv[i] = offset[i];
+  THY_TRY(own->A.upload(A));
+  THY_TRY(own->yiv.upload(yiv));
+  THY_TRY(own->yiv_lin.upload(yiv_lin));
+  THY_TRY(own->off.upload(offv));
+  THY_TRY(own->col.upload(own->col_host));
+  LikDev& v = own->view;
+  v.distribution = distribution;
+  v.link = link;
+  v.jacobian = jacobian;
+  v.n = n;
+  v.dl = dl;
+  v.n_pad = n_pad;
+  v.lds = lds;
+  v.A = own->A.ptr;
+  v.yiv = own->yiv.ptr;
+  v.yiv_lin = own->yiv_lin.ptr;
+  v.off = own->off.ptr;
+  v.col = own->col.ptr;
+  v.log_const = lc;
+  v.differential = differential;
+  v.cauchy_sign = m->opt_cauchy_ref_sign ? 1.0 : -1.0;
+  m->lik_dev.push_back(std::move(own));
   return THY_OK;
 }
 
@@ -371,81 +453,22 @@ thy_status thy_model_finalize(thy_model_t m) {
 
   // ---- likelihoods ----
   for (auto& L : m->liks) {
-    auto own = std::make_unique<LikDevOwner>();
     // blocks in ascending label order (LinearForwardModel.scala:87-101)
     std::vector<int> order(L.labels.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return L.labels[a] < L.labels[b]; });
-    int dl = 0;
-    for (int b : order) dl += L.dims[b];
-    const int n = L.n;
-    const int n_pad = (int)round_up(n, 32);
-    // row pitch = 4 (mod 8) doubles: conflict-free DMMA fragment loads (kernels_fused_dmma.cu)
-    const int nt = fused_nt_for(dl);
-    const int lds = (nt > 0 ? 8 * nt : (int)round_up(dl, 8)) + 4;
-    std::vector<double> A((size_t)n_pad * lds, 0.0);
-    own->col_host.clear();
-    int c0 = 0;
+    std::vector<int> cols;
+    std::vector<const double*> blocks;
+    std::vector<int> widths;
     for (int b : order) {
       auto it = m->layout.find(L.labels[b]);
       if (it == m->layout.end()) return fail(THY_ERR_UNKNOWN_LABEL, "unknown label '" + L.labels[b] + "'");
-      const int w = L.dims[b];
-      for (int j = 0; j < w; ++j) own->col_host.push_back(it->second.first + j);
-      for (int i = 0; i < n; ++i)
-        for (int j = 0; j < w; ++j) A[(size_t)i * lds + c0 + j] = L.blocks[b][(size_t)i * w + j];
-      c0 += w;
+      for (int j = 0; j < L.dims[b]; ++j) cols.push_back(it->second.first + j);
+      blocks.push_back(L.blocks[b].data());
+      widths.push_back(L.dims[b]);
     }
-    own->contiguous = true;
-    for (int k = 1; k < dl; ++k)
-      if (own->col_host[k] != own->col_host[0] + k) own->contiguous = false;
-    std::vector<double2> yiv(n_pad, make_double2(0.0, 0.0)), yiv_lin(n_pad, make_double2(0.0, 0.0));
-    std::vector<double> offv(n_pad, 0.0);
-    double lc = 0.0;
-    if (L.distribution == THY_DIST_UNIFORM) {
-      for (int i = 0; i < n; ++i) {
-        yiv[i] = make_double2(L.meas[i], L.unc[i]);  // (upper, lower)
-        lc -= std::log(L.meas[i] - L.unc[i]);
-      }
-      // padded rows must always pass the bounds test on f = 0
-      for (int i = n; i < n_pad; ++i) yiv[i] = make_double2(1.0, -1.0);
-    } else {
-      double logdet = 0.0, lognorm = n / 2.0 * LOG_2PI;
-      for (int i = 0; i < n; ++i) {
-        const double o = L.has_offset ? L.offset[i] : 0.0;
-        yiv[i] = make_double2(L.meas[i], 1.0 / L.unc[i]);
-        yiv_lin[i] = make_double2(L.meas[i] - o, 1.0 / L.unc[i]);
-        logdet += std::log(L.unc[i]);
-        lognorm += std::log(std::sqrt(L.unc[i]));
-      }
-      if (L.distribution == THY_DIST_GAUSSIAN)
-        lc = -lognorm;
-      else
-        lc = std::lgamma((1 + n) / 2.0) - std::lgamma(0.5) - n / 2.0 * std::log(M_PI) - logdet / 2.0;
-    }
-    if (L.has_offset)
-      for (int i = 0; i < n; ++i) offv[i] = L.offset[i];
-    THY_TRY(own->A.upload(A));
-    THY_TRY(own->yiv.upload(yiv));
-    THY_TRY(own->yiv_lin.upload(yiv_lin));
-    THY_TRY(own->off.upload(offv));
-    THY_TRY(own->col.upload(own->col_host));
-    LikDev& v = own->view;
-    v.distribution = L.distribution;
-    v.link = L.link;
-    v.jacobian = L.jacobian;
-    v.n = n;
-    v.dl = dl;
-    v.n_pad = n_pad;
-    v.lds = lds;
-    v.A = own->A.ptr;
-    v.yiv = own->yiv.ptr;
-    v.yiv_lin = own->yiv_lin.ptr;
-    v.off = own->off.ptr;
-    v.col = own->col.ptr;
-    v.log_const = lc;
-    v.differential = L.differential;
-    v.cauchy_sign = m->opt_cauchy_ref_sign ? 1.0 : -1.0;
-    m->lik_dev.push_back(std::move(own));
+    THY_TRY(build_lik_dev(m, L.distribution, L.link, L.jacobian, L.differential, L.n, cols, blocks, widths, L.meas.data(),
+                          L.unc.data(), L.has_offset ? L.offset.data() : nullptr, nullptr));
     // host copies of the big blocks are no longer needed
     L.blocks.clear();
     L.blocks.shrink_to_fit();

@@ -139,6 +139,15 @@ struct KernelTimer {
 // eval.cu
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false,
                           bool likelihoods_only = false);
+thy_status launch_likelihood(thy_model_s* m, LikDevOwner& owner, int64_t B, const double* X, double* logp, double* grad,
+                             double csign, cudaStream_t s);
+// model.cu
+thy_status build_lik_dev(thy_model_s* m, int distribution, int link, int jacobian, double differential, int n,
+                         const std::vector<int>& cols, const std::vector<const double*>& blocks,
+                         const std::vector<int>& widths, const double* meas, const double* unc, const double* offset,
+                         const double* log_const_override);
+bool cholesky_lower(const std::vector<double>& S, int n, std::vector<double>& L);
+void spd_inverse(const std::vector<double>& L, int n, std::vector<double>& P);
 // sampling.cu
 thy_status sample_priors_dev(thy_model_s* m, int64_t B, uint64_t seed, double* X);
 }
