@@ -161,3 +161,27 @@ def test_hmc_on_the_collapsed_posterior_samples_the_same_distribution():
         assert np.max(np.abs(s.var(0) / np.diag(cov) - 1.0)) < 5.0 * math.sqrt(2.0 / ess)
     col.close()
     post.close()
+
+
+def test_full_size_config3_canonical_against_collapsed_and_oracle():
+    """BASELINE config 3's model at full size (1000-d, 100k observations; A = 800 MB): two device algorithms that
+    share no kernel configuration -- the canonical wide DMMA pass over all 10^5 observations and the collapsed
+    1000-observation term -- must be the same function, and both match the oracle on a slice."""
+    d, n, B = 1000, 100_000, 512
+    prob = linear_gaussian_problem(d, n, seed=20260103)
+    post = _posterior(prob)
+    col = post.collapsed()
+    mean, _, _, _, _ = post.gaussianPosterior()
+    rng = np.random.default_rng(3)
+    X = np.concatenate([mean[None, :] + 0.01 * rng.standard_normal((B // 2, d)), rng.standard_normal((B // 2, d))])
+    lp, g = post.logPdfGradBatch(X)
+    assert post.lastKernelPath == "wide_dmma"
+    lpc, gc = col.logPdfGradBatch(X)
+    assert rel_err_logp(lpc, lp) < TOL and rel_err_grad(gc, g) < TOL
+    want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X[::64], prior_mean=prob["pm"],
+                                              prior_var=prob["pvar"])
+    assert rel_err_logp(lp[::64], want_lp) < TOL and rel_err_grad(g[::64], want_g) < TOL
+    g0 = post.logPdfGradBatch(mean[None, :])[1]
+    assert np.max(np.abs(g0)) < 1e-9 * np.max(np.abs(g))                       # stationary point of the device-built mean
+    col.close()
+    post.close()

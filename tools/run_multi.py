@@ -94,7 +94,7 @@ def main():
         lfm.close()
         post.close()
 
-    if "c4" in todo:
+    if "c4" in todo or "c4full" in todo:
         from oracle import ref_oracle as o
         d = 50
         y = np.random.default_rng(20260104).standard_normal(d)
@@ -142,6 +142,28 @@ def main():
                 "iterations": int(st.iterations), "rounds": int(st.rounds), "seconds": dt}
             slq.close()
             post.close()
+        if "c4full" in todo:
+            # BASELINE config 4 as written: 10^6 live points, run to the engine's own termination, against the analytic value
+            for uniform in (True, False):
+                post = model(uniform)
+                want = (o.analytic_uniform_box_log_evidence(np.full(d, -10.0), np.full(d, 10.0), np.eye(d), y, np.ones(d))
+                        if uniform else o.analytic_gaussian_log_evidence(np.zeros(d), np.full(d, 25.0), np.eye(d), y, np.ones(d)))
+                cfg = t.SlqConfig(poolSize=P, abscissaNumber=8, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                                  sampleParallelism=P // 16, maxIterationCount=int(1.6 * 80 * P), minIterationCount=P)
+                slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=6, comm=comm, constrainedWalkSteps=40)
+                barrier()
+                t0 = time.perf_counter()
+                slq.rebuildSampleSimulation()
+                dt = max_over_ranks(time.perf_counter() - t0)
+                st = slq.stats
+                res["evidence_P1e6_" + ("uniform" if uniform else "gaussian")] = {
+                    "log_evidence": st.log_evidence_mean, "analytic": want, "error": st.log_evidence_mean - want,
+                    "std_over_abscissas": st.log_evidence_std, "H": st.neg_entropy_mean,
+                    "tolerance_5sqrtHoverP": 5 * math.sqrt(max(st.neg_entropy_mean, 0) / P),
+                    "iterations": int(st.iterations), "rounds": int(st.rounds), "seconds": dt,
+                    "likelihood_evals": int(st.likelihood_evaluations)}
+                slq.close()
+                post.close()
         out["c4_slq_50d"] = res
 
     if comm is not None:
