@@ -261,6 +261,7 @@ typedef struct thy_slq_config {
   /* extensions (0 => default) */
   int constrainedWalkSteps;           /* constrained-walk steps per replacement (default 20)                   */
   int keepRetiredPoints;              /* keep retired positions for thy_slq_sample (single GPU)                */
+  int disableFusedWalk;               /* 1 = always use the per-step kernels (diagnostics; same random numbers) */
 } thy_slq_config;
 
 typedef struct thy_slq_stats {
@@ -284,6 +285,9 @@ thy_status thy_slq_destroy(thy_slq_t h);
 thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats);
 /* Run at most n_rounds more rounds of the live phase without draining (the benchmark's loop); *out_converged set. */
 thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged);
+/* The calling rank's live points (host out_x[count * d], out_loglik[count]; either may be NULL) -- the reference's
+ * `samples` map, SlqEngine.scala:120-143.  out_count = live points held by this rank. */
+thy_status thy_slq_live_points(thy_slq_t h, int64_t* out_count, double* out_x, double* out_loglik);
 /* Retired log-likelihoods in retirement order; *out_count receives the total available. */
 thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, int64_t* out_count);
 /* Per-abscissa ln Z_a and H_a of the quadrature so far (QuadratureIntegrator.scala:29-62); [abscissaNumber] each. */

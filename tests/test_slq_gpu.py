@@ -127,6 +127,39 @@ def test_slq_linear_model_gaussian_prior_and_posterior_samples():
     assert abs(got - want) < tol + 0.05
 
 
+@pytest.mark.parametrize("case", ["identity_uniform", "linear_gaussian", "linear_cauchy"])
+def test_slq_fused_walk_kernel_matches_the_per_step_kernels(case):
+    """The one-kernel replacement step (slq_walk.cu: spawn + M steps + commit, walker state in DMMA fragments) against
+    the per-step kernels: same random numbers, same proposals; the log-likelihoods differ only in summation order, so
+    after one round the two live pools coincide except where a 1e-16 difference flips a constraint test."""
+    rng = np.random.default_rng(5)
+    if case == "identity_uniform":
+        d = 7
+        post, y, _ = _identity_model(d, seed=3, uniform=True)
+    else:
+        d, n = 21, 45
+        A = rng.standard_normal((n, d)) / math.sqrt(d)
+        y = A @ rng.standard_normal(d) + 0.3 * rng.standard_normal(n)
+        lik = (t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.6), "theta") if case == "linear_gaussian"
+               else t.CauchyLikelihood.of(A, y, np.full(n, 0.6), "theta"))
+        post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.full(d, 4.0))], [lik])
+    P, K = 4096, 1000                                                        # 1000 walkers: a ragged last group of 8
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=2, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                      sampleParallelism=K, maxIterationCount=50 * P, minIterationCount=P)
+    pools = []
+    for fused in (True, False):
+        slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=77, constrainedWalkSteps=12, fusedWalk=fused)
+        slq.runRounds(1)
+        x, ll = slq.livePoints()
+        pools.append((x, ll, slq.retiredLogLikelihoods()))
+        slq.close()
+    (xa, la, ra), (xb, lb, rb) = pools
+    assert np.array_equal(ra, rb)                                            # the first round retires prior draws
+    same = np.all(xa == xb, axis=1)
+    assert same.mean() > 0.995, same.mean()
+    assert np.max(np.abs(la[same] - lb[same]) / np.maximum(1.0, np.abs(lb[same]))) < 1e-12
+
+
 def test_slq_duplicate_live_points_do_not_break_the_threshold_step():
     """A walker that never moves is an exact copy of a survivor (the reference nudges duplicates by one ulp,
     SlqEngine.scala:107-118); with one walk step per replacement most replacements are copies, so log-likelihood ties

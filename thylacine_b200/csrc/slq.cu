@@ -47,7 +47,17 @@ struct thy_slq_s {
   thy::DevBuf<double> ret_logw;                          // log posterior weight under the expected abscissa
   long long iterations = 0, rounds = 0, evals = 0;
   long long ret_capacity = 0;
+  bool fused_walk = false;             // slq_walk.cu covers this model: one kernel per round instead of 5 per walk step
+  cudaStream_t side = nullptr;         // evidence accumulation runs beside the walk (it only needs the retired values)
+  cudaEvent_t ev_retired = nullptr, ev_evidence = nullptr;
+  double* host_ao = nullptr;           // pinned [A][2] copy of abs_out for the convergence test
   bool finished = false;
+  ~thy_slq_s() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_retired) cudaEventDestroy(ev_retired);
+    if (ev_evidence) cudaEventDestroy(ev_evidence);
+    if (host_ao) cudaFreeHost(host_ao);
+  }
   thy_slq_stats stats{};
 };
 
@@ -152,14 +162,20 @@ __global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, int d, con
     }
   }
 }
-__global__ void k_slq_sigma_final(long long Pl, int d, const double* __restrict__ part, int nslab, double* __restrict__ sigma) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_slq_sigma_final(long long Pl, int d, const double* __restrict__ part, int nslab,
+                                                         double* __restrict__ sigma) {
+  // one warp per dimension; lanes stride the slabs in a fixed order, then a shuffle tree: deterministic
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= d) return;
   double s = 0.0, s2 = 0.0;
-  for (int b = 0; b < nslab; ++b) {
+  for (int b = lane; b < nslab; b += 32) {
     s += part[((size_t)b * 2 + 0) * d + j];
     s2 += part[((size_t)b * 2 + 1) * d + j];
   }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  if (lane != 0) return;
   const double mean = s / Pl;
   const double var = fmax(s2 / Pl - mean * mean, 0.0);
   sigma[j] = sqrt(var);
@@ -192,8 +208,9 @@ __global__ void __launch_bounds__(256) k_slq_propose(int c, int d, uint64_t seed
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)c * d) return;
   const int w = (int)(i / d), j = (int)(i % d);
-  const double z = rng_normal(seed, ((uint64_t)rank << 40) | (uint64_t)w, (uint32_t)j, RNG_SLQ_MOVE, step);
-  Yp[i] = Y[i] + scalars[0] * sigma[j] * z;
+  double z0, z1;
+  rng_normal_pair_fast(seed, ((uint64_t)rank << 40) | (uint64_t)w, slq_move_item(j), RNG_SLQ_MOVE, step, z0, z1);
+  Yp[i] = Y[i] + scalars[0] * sigma[j] * (slq_move_branch(j) ? z1 : z0);
 }
 
 // Metropolis test w.r.t. the prior, hard likelihood constraint L' > L*.
@@ -441,8 +458,8 @@ static thy_status slq_eval(thy_slq_s* h, long long n, const double* X, double* l
   return THY_OK;
 }
 
-static thy_status slq_evidence(thy_slq_s* h, const double* retired_sorted, int Kr, long long n0, int finalize) {
-  cudaStream_t s = h->model->stream;
+static thy_status slq_evidence(thy_slq_s* h, const double* retired_sorted, int Kr, long long n0, int finalize,
+                               cudaStream_t s) {
   const long long stride = std::max<long long>(h->K, h->P);
   k_slq_evidence<<<h->A, EVT, 0, s>>>(Kr, n0, h->iterations, h->seed, retired_sorted, h->tmp_logx.ptr, stride,
                                       h->abs_state.ptr, finalize, h->abs_out.ptr);
@@ -471,7 +488,12 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
   // retired values recorded in global order (identical on every rank)
   if (h->iterations + Kr > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
   THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, merged, (size_t)Kr * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, Kr, h->P, 0));
+  // the evidence update only needs the retired values: it runs on the side stream while the walk replaces the points
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_retired, s));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_retired, 0));
+  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, Kr, h->P, 0, h->side));
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->host_ao, h->abs_out.ptr, (size_t)h->A * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->side));
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_evidence, h->side));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
   if (c > h->K) return fail(THY_ERR_STATE, "SLQ: internal error, retire count exceeds the walker buffers");
   if (c >= h->Pl) return fail(THY_ERR_STATE, "SLQ: a rank lost all of its live points in one round; lower sampleParallelism");
@@ -483,11 +505,17 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
     // per-dimension spread of the live pool sets the walk's proposal shape
     const int nslab = 1184;   // 8 slabs per SM
     k_slq_sigma_part<<<nslab, 256, 0, s>>>(h->Pl, d, h->x.ptr, h->sig_part.ptr, nslab);
-    k_slq_sigma_final<<<(unsigned)ceil_div(d, 128), 128, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
+    k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
+    count_launch(2);
+    if (h->fused_walk) {
+      THY_TRY(launch_slq_walk(m, c, h->Pl, h->M, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr, h->x.ptr, h->ll.ptr,
+                              h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s));
+      h->evals += (long long)c * h->M;
+    } else {
     k_slq_spawn<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, h->Pl, d, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr,
                                                         h->x.ptr, h->ll.ptr, h->lpr.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
                                                         h->slot.ptr);
-    count_launch(3);
+    count_launch();
     for (int step = 0; step < h->M; ++step) {
       const uint64_t gstep = (uint64_t)h->rounds * (uint64_t)h->M + step;
       k_slq_propose<<<(unsigned)ceil_div((long long)c * d, 256), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr,
@@ -499,9 +527,11 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
     }
     k_slq_commit<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->slot.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr, h->x.ptr,
                                                          h->ll.ptr, h->lpr.ptr);
+    count_launch();
+    }
     k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability, c, h->M,
                                    h->accepted.ptr);
-    count_launch(2);
+    count_launch();
   }
   THY_CUDA_CHECK(cudaGetLastError());
   h->iterations += Kr;
@@ -568,6 +598,15 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   }
   cudaStream_t s = m->stream;
   if (st == THY_OK) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_retired, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_evidence, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost(&h->host_ao, (size_t)h->A * 2 * sizeof(double)) != cudaSuccess ||
+        cudaEventRecord(h->ev_evidence, h->side) != cudaSuccess)
+      st = fail(THY_ERR_CUDA, "SLQ side stream setup failed");
+    h->fused_walk = !cfg->disableFusedWalk && slq_walk_supported(m);
+  }
+  if (st == THY_OK) {
     // initial pool: prior draws (+ seeds in the first slots, SlqEngine.scala:384-389,409)
     chk(sample_priors_dev(m, Pl, rng_seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(h->rank + 1)), h->x.ptr));
     if (st == THY_OK && n_seeds > 0 && h->rank == 0) {
@@ -614,10 +653,11 @@ static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* conve
     const int Kr = (int)std::min<long long>(h->K, remaining);
     int c = 0;
     THY_TRY(slq_round(h, Kr, &c));
-    THY_CUDA_CHECK(cudaMemcpyAsync(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+    // the side stream finishes the evidence update long before the walk ends: the host decides on convergence and
+    // queues the next round's sort while the walk is still running
+    THY_CUDA_CHECK(cudaEventSynchronize(h->ev_evidence));
     double hmax = -INFINITY;
-    for (int a = 0; a < h->A; ++a) hmax = std::max(hmax, ao[(size_t)a * 2 + 1]);
+    for (int a = 0; a < h->A; ++a) hmax = std::max(hmax, h->host_ao[(size_t)a * 2 + 1]);
     if (h->iterations > h->cfg.minIterationCount && std::isfinite(hmax) &&
         (double)h->iterations >= 10.0 * (double)h->P * hmax) {
       *converged = true;
@@ -661,7 +701,8 @@ extern "C" thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
                                                             h->ret_x.ptr + (size_t)h->iterations * h->d);
     count_launch();
   }
-  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, (int)h->P, h->P, 1));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_evidence, 0));   // the last round's evidence update (side stream)
+  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, (int)h->P, h->P, 1, s));
   const long long live_iterations = h->iterations;
   h->iterations += h->P;
   std::vector<double> sc(8);
@@ -705,11 +746,22 @@ thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, i
   return THY_OK;
 }
 
+/* The rank's live points and their log-likelihoods (the reference's `samples` map, SlqEngine.scala:120-143). */
+thy_status thy_slq_live_points(thy_slq_t h, int64_t* out_count, double* out_x, double* out_loglik) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (out_count) *out_count = h->Pl;
+  THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
+  if (out_x) THY_CUDA_CHECK(cudaMemcpy(out_x, h->x.ptr, (size_t)h->Pl * h->d * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_loglik) THY_CUDA_CHECK(cudaMemcpy(out_loglik, h->ll.ptr, (size_t)h->Pl * sizeof(double), cudaMemcpyDeviceToHost));
+  return THY_OK;
+}
+
 /* Per-abscissa results of the quadrature so far: ln Z_a and H_a (QuadratureIntegrator.scala:29-62). */
 thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, double* out_neg_entropy) {
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   std::vector<double> ao((size_t)h->A * 2);
   THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
+  THY_CUDA_CHECK(cudaStreamSynchronize(h->side));
   THY_CUDA_CHECK(cudaMemcpy(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost));
   for (int a = 0; a < h->A; ++a) {
     if (out_log_evidence) out_log_evidence[a] = ao[(size_t)a * 2];

@@ -260,7 +260,7 @@ class _SlqConfigC(C.Structure):
     _fields_ = [("poolSize", C.c_int), ("abscissaNumber", C.c_int), ("domainScalingIncrement", C.c_double),
                 ("targetAcceptanceProbability", C.c_double), ("sampleParallelism", C.c_int),
                 ("maxIterationCount", C.c_int), ("minIterationCount", C.c_int), ("constrainedWalkSteps", C.c_int),
-                ("keepRetiredPoints", C.c_int)]
+                ("keepRetiredPoints", C.c_int), ("disableFusedWalk", C.c_int)]
 
 
 class _SlqStatsC(C.Structure):
@@ -277,6 +277,7 @@ register("thy_slq_run_rounds", C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)])
 register("thy_slq_retired", C.c_int, [_vp, C.c_int64, _dp, _i64p])
 register("thy_slq_sample", C.c_int, [_vp, C.c_int, C.c_uint64, _dp])
 register("thy_slq_abscissa_results", C.c_int, [_vp, _dp, _dp])
+register("thy_slq_live_points", C.c_int, [_vp, _i64p, _dp, _dp])
 
 
 @dataclass
@@ -319,7 +320,7 @@ class SlqIntegratedPosterior:
     @classmethod
     def of(cls, slqConfig: SlqConfig, posterior: UnnormalisedPosterior, slqTelemetryUpdateCallback=None,
            domainRebuildStartCallback=None, domainRebuildFinishCallback=None, seedsSpec=None, rngSeed: int = 0,
-           comm=None, constrainedWalkSteps: int = 0, keepRetiredPoints: bool = False):
+           comm=None, constrainedWalkSteps: int = 0, keepRetiredPoints: bool = False, fusedWalk: bool = True):
         self = object.__new__(cls)
         self.posterior, self.config, self.comm = posterior, slqConfig, comm
         self._cb = slqTelemetryUpdateCallback
@@ -327,7 +328,7 @@ class SlqIntegratedPosterior:
         cfg = _SlqConfigC(slqConfig.poolSize, slqConfig.abscissaNumber, float(slqConfig.domainScalingIncrement),
                           float(slqConfig.targetAcceptanceProbability), slqConfig.sampleParallelism,
                           slqConfig.maxIterationCount, slqConfig.minIterationCount, int(constrainedWalkSteps),
-                          1 if keepRetiredPoints else 0)
+                          1 if keepRetiredPoints else 0, 0 if fusedWalk else 1)
         seeds = None
         n_seeds = 0
         if seedsSpec:
@@ -375,6 +376,14 @@ class SlqIntegratedPosterior:
         lz, hh = np.empty(self.config.abscissaNumber), np.empty(self.config.abscissaNumber)
         check(self._lib.thy_slq_abscissa_results(self._h, _ptr(lz), _ptr(hh)))
         return lz, hh
+
+    def livePoints(self):
+        """(points, log-likelihoods) of the live pool held by this rank (SlqEngine.scala:120-143 ``samples``)."""
+        n = C.c_int64()
+        check(self._lib.thy_slq_live_points(self._h, C.byref(n), None, None))
+        x, ll = np.empty((n.value, self.posterior.domainDimension)), np.empty(n.value)
+        check(self._lib.thy_slq_live_points(self._h, C.byref(n), _ptr(x), _ptr(ll)))
+        return x, ll
 
     def retiredLogLikelihoods(self) -> np.ndarray:
         n = C.c_int64()
