@@ -204,6 +204,7 @@ thy_status thy_model_create(thy_model_t* out) {
 }
 
 thy_status thy_model_destroy(thy_model_t m) {
+  if (m && m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m && m->h2d_stream) {
     cudaStreamDestroy(m->h2d_stream);
     cudaStreamDestroy(m->d2h_stream);
@@ -474,6 +475,10 @@ thy_status thy_model_finalize(thy_model_t m) {
     L.blocks.shrink_to_fit();
   }
   THY_CUDA_CHECK(cudaDeviceSynchronize());
+  if (m->stream == 0) {
+    THY_CUDA_CHECK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamDefault));
+    m->stream = m->own_stream;
+  }
   m->finalized = true;
   return THY_OK;
 }
@@ -497,7 +502,7 @@ thy_status thy_model_label_layout(thy_model_t m, const char* label, int* out_off
 
 thy_status thy_model_set_stream(thy_model_t m, void* cuda_stream) {
   if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
-  m->stream = (cudaStream_t)cuda_stream;
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : (m->own_stream ? m->own_stream : (cudaStream_t)0);
   return THY_OK;
 }
 

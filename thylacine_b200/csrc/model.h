@@ -92,6 +92,10 @@ struct thy_model_s {
   int opt_fd_incremental = 0;
   int opt_kernel_path = 0;
   cudaStream_t stream = 0;
+  // Default stream of the handle, created at finalize: a BLOCKING stream, so it keeps the implicit ordering with the
+  // legacy default stream that callers of the *_dev entry points rely on, yet (unlike stream 0) it can be captured
+  // into CUDA graphs.  thy_model_set_stream replaces it.
+  cudaStream_t own_stream = nullptr;
   int device = -1;
   std::map<std::string, std::pair<int, int>> layout;  // label -> (offset, dim)
   // device state

@@ -51,12 +51,32 @@ struct thy_slq_s {
   cudaStream_t side = nullptr;         // evidence accumulation runs beside the walk (it only needs the retired values)
   cudaEvent_t ev_retired = nullptr, ev_evidence = nullptr;
   double* host_ao = nullptr;           // pinned [A][2] copy of abs_out for the convergence test
+  int* host_c = nullptr;               // pinned copy of the local retire count
+  long long* host_it = nullptr;        // pinned staging of `iterations` for the device-side round control
+  thy::DevBuf<long long> ctl;          // [0] iterations at the start of the round (read by graph-captured kernels)
+  cudaGraphExec_t select_graph = nullptr;   // the selection phase of a full round (sigma, sort, gather, merge, threshold)
+  bool use_graph = true;
+  // THY_SLQ_TRACE=1: CUDA-event phase times of the round (sort / gather / merge+threshold / replace), printed at destroy
+  bool trace = false;
+  cudaEvent_t tev[6] = {};
+  double tsum[5] = {0, 0, 0, 0, 0};
+  long long tcount = 0;
   bool finished = false;
   ~thy_slq_s() {
     if (side) cudaStreamDestroy(side);
     if (ev_retired) cudaEventDestroy(ev_retired);
     if (ev_evidence) cudaEventDestroy(ev_evidence);
     if (host_ao) cudaFreeHost(host_ao);
+    if (host_c) cudaFreeHost(host_c);
+    if (host_it) cudaFreeHost(host_it);
+    if (select_graph) cudaGraphExecDestroy(select_graph);
+    if (trace) {
+      if (tcount > 0)
+        std::fprintf(stderr, "[thy slq trace] rank %d: %lld rounds; us/round: sigma %.1f, local sort %.1f, all-gather %.1f, "
+                     "merge+threshold %.1f, replace+adapt %.1f\n", rank, tcount, 1e3 * tsum[0] / tcount, 1e3 * tsum[1] / tcount,
+                     1e3 * tsum[2] / tcount, 1e3 * tsum[3] / tcount, 1e3 * tsum[4] / tcount);
+      for (auto& e : tev) if (e) cudaEventDestroy(e);
+    }
   }
   thy_slq_stats stats{};
 };
@@ -92,6 +112,35 @@ __device__ __forceinline__ long long upper_bound_dev(const double* v, long long 
   }
   return lo;
 }
+// Merge of the ranks' sorted candidate lists: element (r, i) computes its position in the union -- values from lower
+// ranks win ties, then the position inside the list -- and the Kr smallest land in `merged` in ascending order.
+// One launch instead of a radix sort of Kr * world keys.
+__global__ void __launch_bounds__(256) k_slq_merge(const double* __restrict__ cand_all, int Kr, int world,
+                                                   double* __restrict__ merged) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)Kr * world) return;
+  const int r = (int)(e / Kr), i = (int)(e % Kr);
+  const double v = cand_all[e];
+  long long pos = i;
+  for (int q = 0; q < world; ++q) {
+    if (q == r) continue;
+    const double* lst = cand_all + (size_t)q * Kr;
+    // the smallest value of a list that is already beyond v contributes nothing; skip its search
+    if (lst[0] > v) continue;
+    pos += (q < r) ? upper_bound_dev(lst, Kr, v) : lower_bound_dev(lst, Kr, v);
+    if (pos >= Kr) return;
+  }
+  if (pos < Kr) merged[pos] = v;
+}
+
+// retired values recorded in global order at ret_ll[iterations ...] (iterations read from the device-side control
+// word so that the launch can live inside a CUDA graph)
+__global__ void __launch_bounds__(256) k_slq_copy_retired(const double* __restrict__ merged, int Kr,
+                                                          const long long* __restrict__ ctl, double* __restrict__ ret_ll) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Kr) ret_ll[ctl[0] + i] = merged[i];
+}
+
 __global__ void k_slq_threshold(const double* __restrict__ merged, int Kr, const double* __restrict__ local_sorted,
                                 const double* __restrict__ cand_all, int world, int rank,
                                 double* __restrict__ scalars, int* __restrict__ count) {
@@ -433,7 +482,6 @@ static thy_status slq_sort_local(thy_slq_s* h) {
   THY_TRY(h->cub_tmp.reserve(bytes));
   THY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.ptr, bytes, h->keys_in.ptr, h->keys_out.ptr, h->idx_in.ptr,
                                                  h->idx_out.ptr, (int)h->Pl, 0, 64, s));
-  count_launch(3);
   return THY_OK;
 }
 
@@ -468,26 +516,81 @@ static thy_status slq_evidence(thy_slq_s* h, const double* retired_sorted, int K
   return THY_OK;
 }
 
-static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
-  thy_model_s* m = h->model;
-  cudaStream_t s = m->stream;
+// Selection phase of a round: proposal spread of the live pool, local sort, exchange of each rank's Kr smallest, merge,
+// threshold and local retire count, retired values appended.  Every launch has round-independent arguments (the
+// append position comes from h->ctl), so a full round's selection phase is captured once as a CUDA graph and replayed:
+// ~25 launches become one, which is what keeps 8 ranks from being host-launch bound.
+static thy_status slq_select_phase(thy_slq_s* h, int Kr, cudaStream_t s, bool tracing) {
   const int d = h->d;
+  if (tracing) cudaEventRecord(h->tev[0], s);
+  const int nslab = 1184;   // 8 slabs per SM
+  k_slq_sigma_part<<<nslab, 256, 0, s>>>(h->Pl, d, h->x.ptr, h->sig_part.ptr, nslab);
+  k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
+  if (tracing) cudaEventRecord(h->tev[1], s);
   THY_TRY(slq_sort_local(h));
+  if (tracing) cudaEventRecord(h->tev[2], s);
   // each rank contributes its Kr smallest; the Kr globally smallest are retired
   const double* merged = h->keys_out.ptr;
   if (h->world > 1) {
     THY_TRY(comm_all_gather_f64(h->comm, h->keys_out.ptr, h->cand_all.ptr, (size_t)Kr, s));
-    THY_TRY(slq_sort_keys(h, h->cand_all.ptr, h->cand_sorted.ptr, Kr * h->world));
+    if (tracing) cudaEventRecord(h->tev[3], s);
+    k_slq_merge<<<(unsigned)ceil_div((long long)Kr * h->world, 256), 256, 0, s>>>(h->cand_all.ptr, Kr, h->world,
+                                                                                 h->cand_sorted.ptr);
     merged = h->cand_sorted.ptr;
+  } else if (tracing) {
+    cudaEventRecord(h->tev[3], s);
   }
   k_slq_threshold<<<1, 32, 0, s>>>(merged, Kr, h->keys_out.ptr, h->cand_all.ptr, h->world, h->rank, h->scalars.ptr,
                                    h->count_dev.ptr);
-  count_launch();
-  int c = 0;
-  THY_CUDA_CHECK(cudaMemcpyAsync(&c, h->count_dev.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-  // retired values recorded in global order (identical on every rank)
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->host_c, h->count_dev.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  k_slq_copy_retired<<<(unsigned)ceil_div(Kr, 256), 256, 0, s>>>(merged, Kr, h->ctl.ptr, h->ret_ll.ptr);
+  if (tracing) cudaEventRecord(h->tev[4], s);
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
+}
+
+static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
+  thy_model_s* m = h->model;
+  cudaStream_t s = m->stream;
+  const int d = h->d;
+  if (h->trace && h->rounds > 0) {   // the previous round's events have all completed or will by the sync below
+    cudaEventSynchronize(h->tev[5]);
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]) == cudaSuccess) h->tsum[i] += ms;
+    }
+    h->tcount += 1;
+  }
   if (h->iterations + Kr > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
-  THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, merged, (size_t)Kr * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  *h->host_it = h->iterations;   // the previous round's copy of this word completed before its sync returned
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->ctl.ptr, h->host_it, sizeof(long long), cudaMemcpyHostToDevice, s));
+  const bool graphable = h->use_graph && !h->trace && s != 0 && Kr == h->K && h->rounds > 0;   // round 0 sizes the sort scratch
+  if (graphable && !h->select_graph) {
+    cudaGraph_t g = nullptr;
+    THY_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    thy_status st = slq_select_phase(h, Kr, s, false);
+    cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (st != THY_OK || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      h->use_graph = false;   // capture unsupported here (e.g. a collective library without graph support): plain launches
+    } else {
+      ce = cudaGraphInstantiate(&h->select_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) {
+        cudaGetLastError();
+        h->select_graph = nullptr;
+        h->use_graph = false;
+      }
+    }
+  }
+  const int select_launches = 2 + 11 + (h->world > 1 ? 2 : 0) + 2;
+  if (graphable && h->select_graph) {
+    THY_CUDA_CHECK(cudaGraphLaunch(h->select_graph, s));
+  } else {
+    THY_TRY(slq_select_phase(h, Kr, s, h->trace));
+  }
+  count_launch(select_launches);
   // the evidence update only needs the retired values: it runs on the side stream while the walk replaces the points
   THY_CUDA_CHECK(cudaEventRecord(h->ev_retired, s));
   THY_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_retired, 0));
@@ -495,6 +598,7 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
   THY_CUDA_CHECK(cudaMemcpyAsync(h->host_ao, h->abs_out.ptr, (size_t)h->A * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->side));
   THY_CUDA_CHECK(cudaEventRecord(h->ev_evidence, h->side));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int c = *h->host_c;
   if (c > h->K) return fail(THY_ERR_STATE, "SLQ: internal error, retire count exceeds the walker buffers");
   if (c >= h->Pl) return fail(THY_ERR_STATE, "SLQ: a rank lost all of its live points in one round; lower sampleParallelism");
   if (h->cfg.keepRetiredPoints && h->world == 1 && c > 0) {
@@ -502,11 +606,6 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
     count_launch();
   }
   if (c > 0) {
-    // per-dimension spread of the live pool sets the walk's proposal shape
-    const int nslab = 1184;   // 8 slabs per SM
-    k_slq_sigma_part<<<nslab, 256, 0, s>>>(h->Pl, d, h->x.ptr, h->sig_part.ptr, nslab);
-    k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
-    count_launch(2);
     if (h->fused_walk) {
       THY_TRY(launch_slq_walk(m, c, h->Pl, h->M, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr, h->x.ptr, h->ll.ptr,
                               h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s));
@@ -533,6 +632,7 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
                                    h->accepted.ptr);
     count_launch();
   }
+  if (h->trace) cudaEventRecord(h->tev[5], s);
   THY_CUDA_CHECK(cudaGetLastError());
   h->iterations += Kr;
   h->rounds += 1;
@@ -602,9 +702,19 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
         cudaEventCreateWithFlags(&h->ev_retired, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_evidence, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost(&h->host_ao, (size_t)h->A * 2 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&h->host_c, sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&h->host_it, sizeof(long long)) != cudaSuccess ||
         cudaEventRecord(h->ev_evidence, h->side) != cudaSuccess)
       st = fail(THY_ERR_CUDA, "SLQ side stream setup failed");
     h->fused_walk = !cfg->disableFusedWalk && slq_walk_supported(m);
+    chk(h->ctl.reserve(1));
+    const char* ng = std::getenv("THY_SLQ_GRAPH");
+    h->use_graph = !(ng && ng[0] == '0');
+    const char* tr = std::getenv("THY_SLQ_TRACE");
+    h->trace = tr && tr[0] == '1';
+    if (h->trace)
+      for (auto& e : h->tev)
+        if (cudaEventCreate(&e) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ trace events");
   }
   if (st == THY_OK) {
     // initial pool: prior draws (+ seeds in the first slots, SlqEngine.scala:384-389,409)
