@@ -20,6 +20,7 @@
 #include <cub/cub.cuh>
 #include <cmath>
 #include <algorithm>
+#include <chrono>
 
 struct thy_slq_s {
   thy_model_s* model = nullptr;
@@ -61,6 +62,11 @@ struct thy_slq_s {
   cudaEvent_t tev[6] = {};
   double tsum[5] = {0, 0, 0, 0, 0};
   long long tcount = 0;
+  // THY_SLQ_TRACE=2: host wall-clock split of the round (graph replay stays on): enqueue / wait for the retire count /
+  // enqueue of the replacement step / wait for the evidence update
+  bool htrace = false;
+  double hsum[4] = {0, 0, 0, 0};
+  long long hcount = 0;
   bool finished = false;
   ~thy_slq_s() {
     if (side) cudaStreamDestroy(side);
@@ -70,6 +76,10 @@ struct thy_slq_s {
     if (host_c) cudaFreeHost(host_c);
     if (host_it) cudaFreeHost(host_it);
     if (select_graph) cudaGraphExecDestroy(select_graph);
+    if (htrace && hcount > 0)
+      std::fprintf(stderr, "[thy slq host trace] rank %d: %lld rounds, graph %s; host us/round: enqueue selection %.1f, wait count %.1f, "
+                   "enqueue replacement %.1f, wait evidence %.1f\n", rank, hcount, select_graph ? "on" : "off",
+                   1e6 * hsum[0] / hcount, 1e6 * hsum[1] / hcount, 1e6 * hsum[2] / hcount, 1e6 * hsum[3] / hcount);
     if (trace) {
       if (tcount > 0)
         std::fprintf(stderr, "[thy slq trace] rank %d: %lld rounds; us/round: sigma %.1f, local sort %.1f, all-gather %.1f, "
@@ -562,6 +572,7 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
     h->tcount += 1;
   }
   if (h->iterations + Kr > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
+  const auto ht0 = std::chrono::steady_clock::now();
   *h->host_it = h->iterations;   // the previous round's copy of this word completed before its sync returned
   THY_CUDA_CHECK(cudaMemcpyAsync(h->ctl.ptr, h->host_it, sizeof(long long), cudaMemcpyHostToDevice, s));
   const bool graphable = h->use_graph && !h->trace && s != 0 && Kr == h->K && h->rounds > 0;   // round 0 sizes the sort scratch
@@ -597,7 +608,9 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
   THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, Kr, h->P, 0, h->side));
   THY_CUDA_CHECK(cudaMemcpyAsync(h->host_ao, h->abs_out.ptr, (size_t)h->A * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->side));
   THY_CUDA_CHECK(cudaEventRecord(h->ev_evidence, h->side));
+  const auto ht1 = std::chrono::steady_clock::now();
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  const auto ht2 = std::chrono::steady_clock::now();
   const int c = *h->host_c;
   if (c > h->K) return fail(THY_ERR_STATE, "SLQ: internal error, retire count exceeds the walker buffers");
   if (c >= h->Pl) return fail(THY_ERR_STATE, "SLQ: a rank lost all of its live points in one round; lower sampleParallelism");
@@ -633,6 +646,13 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
     count_launch();
   }
   if (h->trace) cudaEventRecord(h->tev[5], s);
+  if (h->htrace) {
+    const auto ht3 = std::chrono::steady_clock::now();
+    h->hsum[0] += std::chrono::duration<double>(ht1 - ht0).count();
+    h->hsum[1] += std::chrono::duration<double>(ht2 - ht1).count();
+    h->hsum[2] += std::chrono::duration<double>(ht3 - ht2).count();
+    h->hcount += 1;
+  }
   THY_CUDA_CHECK(cudaGetLastError());
   h->iterations += Kr;
   h->rounds += 1;
@@ -674,7 +694,9 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   h->A = cfg->abscissaNumber;
   h->M = cfg->constrainedWalkSteps > 0 ? cfg->constrainedWalkSteps : 20;
   int K = cfg->sampleParallelism > 0 ? cfg->sampleParallelism : 1;
-  K = (int)std::min<long long>(K, std::max<long long>(1, h->Pl / 4));   // every rank must keep survivors
+  // every rank contributes its K smallest and must keep survivors to spawn from: K <= half of a rank's pool (a rank
+  // holds ~K / world of a round's retirees; one that would lose its whole pool is reported as an error)
+  K = (int)std::min<long long>(K, std::max<long long>(1, h->Pl / 2));
   h->K = K;
   h->ret_capacity = (long long)cfg->maxIterationCount + K + h->P;
   const int d = h->d;
@@ -712,6 +734,7 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     h->use_graph = !(ng && ng[0] == '0');
     const char* tr = std::getenv("THY_SLQ_TRACE");
     h->trace = tr && tr[0] == '1';
+    h->htrace = tr && tr[0] == '2';
     if (h->trace)
       for (auto& e : h->tev)
         if (cudaEventCreate(&e) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ trace events");
@@ -765,7 +788,9 @@ static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* conve
     THY_TRY(slq_round(h, Kr, &c));
     // the side stream finishes the evidence update long before the walk ends: the host decides on convergence and
     // queues the next round's sort while the walk is still running
+    const auto hw0 = std::chrono::steady_clock::now();
     THY_CUDA_CHECK(cudaEventSynchronize(h->ev_evidence));
+    if (h->htrace) h->hsum[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - hw0).count();
     double hmax = -INFINITY;
     for (int a = 0; a < h->A; ++a) hmax = std::max(hmax, h->host_ao[(size_t)a * 2 + 1]);
     if (h->iterations > h->cfg.minIterationCount && std::isfinite(hmax) &&

@@ -396,7 +396,9 @@ class SlqIntegratedPosterior:
         """QuadratureIntegrator.getIntegrationStats (QuadratureIntegrator.scala:64-83) under the expected abscissa:
         sum_i w_i integrand(L_i) with L_i = exp(l_i - max l).  ``integrand`` maps an array of scaled likelihoods."""
         ll = self.retiredLogLikelihoods()
-        P, K, live = self.config.poolSize, max(1, min(self.config.sampleParallelism, self.config.poolSize // 4)), int(self.stats.iterations)
+        world = self.comm.world if self.comm is not None else 1
+        P, live = self.config.poolSize, int(self.stats.iterations)
+        K = max(1, min(self.config.sampleParallelism, (P // world) // 2))      # the engine's clamp (thy_slq_create)
         j = np.where(np.arange(ll.size) < live, np.arange(ll.size) % K, np.arange(ll.size) - live)
         lx = np.concatenate([[0.0], np.cumsum(-1.0 / (P - j))])[:-1]
         X = np.exp(lx)
