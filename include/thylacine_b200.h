@@ -39,6 +39,7 @@ typedef struct thy_model_s* thy_model_t;
 typedef struct thy_hmc_s* thy_hmc_t;
 typedef struct thy_lfm_s* thy_lfm_t;
 typedef struct thy_slq_s* thy_slq_t;
+typedef struct thy_surface_s* thy_surface_t;
 
 /* ---- library ------------------------------------------------------------------------------------- */
 const char* thy_version(void);
@@ -294,6 +295,24 @@ thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, i
 thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, double* out_neg_entropy);
 /* sample(n) (SamplingSimulation.scala:41-101): posterior resampling of retired points; needs keepRetiredPoints. */
 thy_status thy_slq_sample(thy_slq_t h, int n, uint64_t rng_seed, double* out_samples);
+
+/* ---- CartesianSurface (visualisation/CartesianSurface.scala:30-200) --------------------------------------
+ * CartesianSurface.of(xAbscissa, yAbscissa, callbacks): a grid of values[ix * ny + iy], zero-initialised (:85-88).
+ * add_samples = addSamples(abscissa, samples, ds, kernelVariance) (:129-150): every sample curve (abscissa_i, value_i)
+ * is resampled at arc-length spacing ds (SimplexChain.scala:21-33, Simplex.scala:25-47; the remainder carries across
+ * segments; the point the reference's getPoints drops is dropped here too) and every grid point gains
+ * sum_p exp(-0.5 * ((px - gx)^2 / xScale^2 + (py - gy)^2 / yScale^2) / kernelVariance)   (:110-127, GraphPoint.scala:26-31).
+ * results = getResults (:152-157): normalise_columns != 0 divides every x column by its trapezoid integral over y
+ * when that is positive (:53-83, MathOps.scala:26-55; repeated y values or ny < 2 -> THY_ERR_INVALID_ARGUMENT where
+ * the reference throws).  samples: host [n_samples * m] row-major; *_dev takes a device pointer (e.g. a sampler's
+ * output buffer) and synchronises the device first.  Progress callbacks are the shim's business. */
+thy_status thy_surface_create(int nx, const double* x_abscissa, int ny, const double* y_abscissa, thy_surface_t* out);
+thy_status thy_surface_destroy(thy_surface_t s);
+thy_status thy_surface_add_samples(thy_surface_t s, int m, const double* abscissa, int64_t n_samples, const double* samples,
+                                   double ds, double kernel_variance);
+thy_status thy_surface_add_samples_dev(thy_surface_t s, int m, const double* abscissa, int64_t n_samples,
+                                       const double* samples_dev, double ds, double kernel_variance);
+thy_status thy_surface_results(thy_surface_t s, int normalise_columns, double* out_values);
 
 /* Measurement hook: when enabled, a CUDA-event pair is recorded on the model's stream around the dominant kernel of
  * every evaluation; thy_model_kernel_time synchronises, returns the summed duration and launch count, and resets. */

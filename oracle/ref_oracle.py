@@ -720,3 +720,84 @@ def log_sum_exp_evidence(logps: Sequence[float], weights: Sequence[float]) -> fl
     a = l[keep] + np.log(w[keep])
     m = np.max(a)
     return float(m + math.log(np.sum(np.exp(a - m))))
+
+
+# --------------------------------------------------------------------------------------------
+# CartesianSurface  (visualisation/CartesianSurface.scala:30-200, SimplexChain.scala:19-45,
+# Simplex.scala:21-53, GraphPoint.scala:20-47, util/MathOps.scala:26-55) -- literal restatement
+# --------------------------------------------------------------------------------------------
+def simplex_interpolation_points(p0, p1, start: float, ds: float):
+    """Simplex.getInterpolationPoints (Simplex.scala:36-47): points at start, start+ds, ... < length, PREPENDED
+    (so the list comes back reversed), and the remainder start - length."""
+    length = math.sqrt((p0[0] - p1[0]) ** 2 + (p0[1] - p1[1]) ** 2)        # GraphPoint.distanceTo
+    prev: List[Tuple[float, float]] = []
+    while not (start >= length):
+        t = start / length
+        if t <= 0:
+            pt = p0
+        elif t >= 1:
+            pt = p1
+        else:
+            pt = (p0[0] + t * (p1[0] - p0[0]), p0[1] + t * (p1[1] - p0[1]))
+        prev = [pt] + prev
+        start = start + ds
+    return prev, start - length
+
+
+def simplex_chain_points(abscissa, values, ds: float) -> List[Tuple[float, float]]:
+    """SimplexChain(points).linearInterpolationUsing(ds).getPoints (SimplexChain.scala:19-45): the interpolated points
+    are wrapped in a new chain of simplexes, whose getPoints is every simplex START -- the last point is dropped, and a
+    chain of fewer than two points is empty."""
+    pts = list(zip([float(a) for a in abscissa], [float(v) for v in values]))
+    if len(pts) < 2:
+        return []
+    carry, out = 0.0, []
+    for p0, p1 in zip(pts[:-1], pts[1:]):
+        seg, carry = simplex_interpolation_points(p0, p1, carry, ds)
+        out = out + seg
+    if len(out) < 2:
+        return []
+    return out[:-1]
+
+
+def trapezoidal_quadrature(abscissa, values) -> float:
+    """MathOps.trapezoidalQuadrature (MathOps.scala:26-55)."""
+    pairs = list(zip([float(a) for a in abscissa], [float(v) for v in values]))
+    if not (len(pairs) > 1 and len({p[0] for p in pairs}) == len(pairs)):
+        raise RuntimeError("Malformed abscissa for trapezoidal quadrature")
+    pairs.sort(key=lambda p: p[0])
+    return sum(0.5 * (a[1] + b[1]) * (b[0] - a[0]) for a, b in zip(pairs[:-1], pairs[1:]))
+
+
+class CartesianSurface:
+    """CartesianSurface.of / addSamples / getResults, one grid point and one curve point at a time."""
+
+    def __init__(self, x_abscissa, y_abscissa):
+        self.x = [float(v) for v in x_abscissa]
+        self.y = [float(v) for v in y_abscissa]
+        self.x_scale = max(self.x) - min(self.x)                             # :40-41
+        self.y_scale = max(self.y) - min(self.y)
+        self.values = {(gx, gy): 0.0 for gx in self.x for gy in self.y}      # zeroValuesSpec :85-88
+
+    def add_samples(self, abscissa, samples, ds: float, kernel_variance: float) -> None:
+        for curve in samples:                                                # :139-143, one addValues per sample
+            pts = simplex_chain_points(abscissa, curve, ds)
+            for g in self.values:                                            # concatenateMapping :110-127
+                acc = self.values[g]
+                for p in pts:
+                    sd = ((p[0] - g[0]) / self.x_scale) ** 2 + ((p[1] - g[1]) / self.y_scale) ** 2
+                    acc = acc + math.exp(-0.5 * sd / kernel_variance)
+                self.values[g] = acc
+
+    def get_results(self) -> Dict[Tuple[float, float], float]:
+        out = {}
+        for gx in self.x:                                                    # normaliseColumns :53-83
+            col = [self.values[(gx, gy)] for gy in self.y]
+            integration = trapezoidal_quadrature(self.y, col)
+            for gy, v in zip(self.y, col):
+                out[(gx, gy)] = v / integration if integration > 0 else v
+        return out
+
+    def results_array(self, normalise: bool = True) -> np.ndarray:
+        src = self.get_results() if normalise else self.values
+        return np.array([[src[(gx, gy)] for gy in self.y] for gx in self.x])

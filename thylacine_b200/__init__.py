@@ -19,3 +19,4 @@ from .optimisers import (  # noqa: F401,E402
     HookeAndJeevesConfig, HookeAndJeevesOptimisedPosterior, MdsConfig, MdsOptimisedPosterior, OptimisationTelemetryUpdate,
 )
 from .analytic import GaussianAnalyticPosterior  # noqa: F401,E402
+from .visualisation import CartesianSurface  # noqa: F401,E402
