@@ -352,6 +352,41 @@ def run_ours(args):
     except Exception as e:  # the canonical line must not be lost to the side-by-side leg
         reduced = {"error": repr(e)}
 
+    # ---- the second half of BASELINE.json's metric: HMC leapfrog steps/s on the same model (one leapfrog step = one
+    # position update of one chain = one gradient evaluation); chains resident on the device
+    hmc_line = None
+    try:
+        import math
+        L_STEPS = 16
+        sigma = 0.1
+        eps = 0.2 * sigma * math.sqrt(D / N_OBS)
+        cfg = t.HmcmcConfig(stepsBetweenSamples=1, stepsInDynamicsSimulation=L_STEPS, warmupStepCount=5,
+                            dynamicsSimulationStepSize=eps)
+        hmc = t.HmcmcSampledPosterior(cfg, post, numberOfChains=CHAINS, rngSeed=2 + rank, seed={"theta": prob["theta"]})
+        hmc.burnIn()
+        ntraj = max(5, min(40, args.steps // 8))
+        hmc.runTrajectories(3)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        hmc.runTrajectories(ntraj)
+        h1.record(stream)
+        barrier()
+        ht = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ht, op=dist.ReduceOp.MAX)
+        hsec = float(ht.item()) * 1e-3
+        att, acc, _ = hmc.stats()
+        steps_total = world * CHAINS * ntraj * L_STEPS
+        hmc_line = {"metric": "HMC leapfrog steps/sec", "value": steps_total / hsec, "unit": "steps/s",
+                    "chains_per_gpu": CHAINS, "trajectories": ntraj, "leapfrog_steps_per_trajectory": L_STEPS,
+                    "step_size": eps, "acceptance_rank0": float(acc.sum() / max(att.sum(), 1)),
+                    "tflops_canonical_per_gpu": CHAINS * ntraj * L_STEPS * FLOPS_PER_EVAL / hsec / 1e12,
+                    "note": "fused leapfrog/Metropolis kernels + the fused DMMA gradient, one CUDA-graph launch per trajectory"}
+        hmc.close()
+    except Exception as e:  # the evals/s line must not be lost to the HMC leg
+        hmc_line = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = load_fp64_peak()
         k_avg_ms = k_ms.value / max(k_n.value, 1)
@@ -389,6 +424,7 @@ def run_ours(args):
                          "flops_per_launch": FLOPS_PER_EVAL * CHAINS, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "reduced_flop": reduced,
+            "hmc": hmc_line,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
