@@ -11,8 +11,9 @@
  *   - a handle is used by one caller at a time; distinct handles may be used concurrently;
  *   - the library owns all device memory; callers own host buffers; inputs are copied at add / finalize;
  *   - there is NO CPU fallback: every evaluation entry point returns THY_ERR_NO_DEVICE without a GPU;
- *   - *_dev variants take device pointers on the current CUDA device and are asynchronous on the
- *     stream set by thy_model_set_stream (default: the legacy default stream).
+ *   - *_dev variants take device pointers on the current CUDA device and are asynchronous on the model's
+ *     stream: by default a blocking stream the handle creates at finalize (ordered with the legacy default
+ *     stream like stream 0 itself, but capturable into CUDA graphs), or the one set by thy_model_set_stream.
  */
 #ifndef THYLACINE_B200_H
 #define THYLACINE_B200_H
@@ -178,7 +179,7 @@ typedef struct thy_hmcmc_config {
 thy_status thy_hmc_create(thy_model_t m, const thy_hmcmc_config* cfg, int64_t n_chains, uint64_t rng_seed,
                           const double* seed_points, thy_hmc_t* out);
 thy_status thy_hmc_destroy(thy_hmc_t h);
-/* Replay one trajectory from a CUDA graph (default on; needs a non-default stream set on the model). */
+/* Replay one trajectory from a CUDA graph (default on; off when the model was given the legacy stream 0 itself). */
 thy_status thy_hmc_set_use_graph(thy_hmc_t h, int enable);
 /* burnIn (HmcmcEngine.scala:180-197): (re)initialise the chains and run warmupStepCount + 1 trajectories. */
 thy_status thy_hmc_burn_in(thy_hmc_t h);
