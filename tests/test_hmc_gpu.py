@@ -109,3 +109,26 @@ def test_hmc_uses_correct_cauchy_sign():
     hmc = t.HmcmcSampledPosterior(cfg, post, seed=np.tile(theta + 0.3, (64, 1)), numberOfChains=64, rngSeed=5)
     s = hmc.sampleChains(4).reshape(-1, d)
     assert np.max(np.abs(s.mean(0) - theta)) < 0.05
+
+
+def test_hmc_graph_survives_workspace_growth_on_the_same_posterior():
+    """A captured trajectory graph holds the addresses of the model's workspace buffers.  An unrelated, larger
+    evaluation on the same posterior re-allocates them; the sampler must notice (workspace epoch) and re-capture
+    instead of replaying stale pointers.  Same seed with and without the interleaved evaluation => identical chains."""
+    d, n, B = 16, 400, 256
+    prob = linear_gaussian_problem(d, n, seed=9)
+    cfg = t.HmcmcConfig(stepsBetweenSamples=1, stepsInDynamicsSimulation=6, warmupStepCount=3, dynamicsSimulationStepSize=0.01)
+    states = []
+    for disturb in (False, True):
+        post, _ = _posteriors(prob)
+        hmc = t.HmcmcSampledPosterior(cfg, post, numberOfChains=B, rngSeed=11, seed={"theta": prob["theta"]})
+        hmc.burnIn()
+        hmc.runTrajectories(3)                                   # graph captured and replayed
+        if disturb:
+            big = np.random.default_rng(1).standard_normal((40 * B, d))
+            post.logPdfGradBatch(big)                            # grows X / logp / grad staging and the ticket array
+        hmc.runTrajectories(4)
+        states.append(hmc.state())
+        hmc.close()
+        post.close()
+    assert np.array_equal(states[0][0], states[1][0]) and np.array_equal(states[0][1], states[1][1])

@@ -40,6 +40,7 @@ template <typename T>
 struct DevBuf {
   T* ptr = nullptr;
   size_t count = 0;
+  uint64_t* realloc_counter = nullptr;   // bumped whenever the buffer moves (captured CUDA graphs hold the old pointer)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -53,6 +54,7 @@ struct DevBuf {
   thy_status reserve(size_t n) {
     if (n <= count) return THY_OK;
     release();
+    if (realloc_counter) ++*realloc_counter;
     THY_CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
     count = n;
     return THY_OK;

@@ -29,6 +29,8 @@ struct thy_hmc_s {
   uint64_t init_epoch = 0;                        // distinguishes prior draws of successive sample() calls
   bool initialised = false;
   cudaGraphExec_t graph = nullptr;                // one trajectory
+  uint64_t graph_ws_epoch = 0;                    // model workspace epoch and stream the graph was captured with
+  cudaStream_t graph_stream = nullptr;
   uint64_t graph_launches = 0;                    // kernels inside the captured trajectory
   bool use_graph = true;
   ~thy_hmc_s() {
@@ -187,6 +189,11 @@ static thy_status hmc_trajectory_launch(thy_hmc_s* h) {
 static thy_status hmc_trajectory(thy_hmc_s* h) {
   cudaStream_t s = h->model->stream;
   if (!h->use_graph || s == 0 /* legacy stream cannot be captured */) return hmc_trajectory_launch(h);
+  if (h->graph && (h->graph_ws_epoch != h->model->ws.epoch || h->graph_stream != s)) {
+    // another evaluation on this model grew a workspace buffer (or the stream changed): the captured addresses are stale
+    cudaGraphExecDestroy(h->graph);
+    h->graph = nullptr;
+  }
   if (!h->graph) {
     // warm every code path (workspace allocation, cudaFuncSetAttribute) outside capture
     THY_TRY(hmc_trajectory_launch(h));
@@ -212,6 +219,8 @@ static thy_status hmc_trajectory(thy_hmc_s* h) {
       h->use_graph = false;
       return hmc_trajectory_launch(h);
     }
+    h->graph_ws_epoch = h->model->ws.epoch;
+    h->graph_stream = s;
     return THY_OK;  // the warm-up launch above was this call's trajectory
   }
   THY_CUDA_CHECK(cudaGraphLaunch(h->graph, s));

@@ -79,6 +79,16 @@ struct Workspace {  // grow-only scratch owned by the model, reused across evalu
   DevBuf<double> XT;                    // wide path: packed / tiled chain vectors
   DevBuf<unsigned int> ticket;          // streaming kernel: last-CTA ticket, zero between launches
   DevBuf<unsigned int> fused_tickets;   // fused kernel: per (tile, warp) segment tickets, zero between launches
+  // Number of times any of the buffers above has moved.  A CUDA graph captured over an evaluation holds their
+  // addresses: its owner compares this epoch before every replay and re-captures when it has changed.
+  uint64_t epoch = 0;
+  Workspace() {
+    X.realloc_counter = logp.realloc_counter = grad.realloc_counter = W.realloc_counter = partG.realloc_counter =
+        partL.realloc_counter = Z.realloc_counter = XT.realloc_counter = &epoch;
+    ticket.realloc_counter = fused_tickets.realloc_counter = &epoch;
+  }
+  Workspace(const Workspace&) = delete;
+  Workspace& operator=(const Workspace&) = delete;
 };
 
 }  // namespace thy

@@ -55,6 +55,7 @@ struct thy_slq_s {
   int* host_c = nullptr;               // pinned copy of the local retire count
   long long* host_it = nullptr;        // pinned staging of `iterations` for the device-side round control
   thy::DevBuf<long long> ctl;          // [0] iterations at the start of the round (read by graph-captured kernels)
+  cudaStream_t select_graph_stream = nullptr;
   cudaGraphExec_t select_graph = nullptr;   // the selection phase of a full round (sigma, sort, gather, merge, threshold)
   bool use_graph = true;
   // THY_SLQ_TRACE=1: CUDA-event phase times of the round (sort / gather / merge+threshold / replace), printed at destroy
@@ -576,7 +577,12 @@ static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
   *h->host_it = h->iterations;   // the previous round's copy of this word completed before its sync returned
   THY_CUDA_CHECK(cudaMemcpyAsync(h->ctl.ptr, h->host_it, sizeof(long long), cudaMemcpyHostToDevice, s));
   const bool graphable = h->use_graph && !h->trace && s != 0 && Kr == h->K && h->rounds > 0;   // round 0 sizes the sort scratch
+  if (h->select_graph && h->select_graph_stream != s) {   // the model was moved to another stream: re-capture
+    cudaGraphExecDestroy(h->select_graph);
+    h->select_graph = nullptr;
+  }
   if (graphable && !h->select_graph) {
+    h->select_graph_stream = s;
     cudaGraph_t g = nullptr;
     THY_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     thy_status st = slq_select_phase(h, Kr, s, false);
