@@ -3,6 +3,7 @@
 // Order: priors initialise logp / grad, then each likelihood term adds its contribution (the reference sums
 // priors first, likelihoods after, left to right -- SURVEY Q7).
 #include "kernels.h"
+#include <algorithm>
 
 namespace thy {
 
@@ -74,9 +75,11 @@ static thy_status ensure_copy_streams(thy_model_s* m) {
   return THY_OK;
 }
 
-// Host-buffer entry point.  Large batches are cut into up to 4 chunks: the H2D copy of chunk k+1 and the D2H copy of
-// chunk k-1 run on their own streams while the kernels of chunk k execute (pinned host buffers make the copies truly
-// asynchronous; pageable buffers still work, just without overlap).
+// Host-buffer entry point.  Large batches are cut into chunks: the H2D copy of chunk k+1 and the D2H copy of chunk k-1
+// run on their own streams while the kernels of chunk k execute (pinned host buffers make the copies truly asynchronous;
+// pageable buffers still work, just without overlap).  What cannot be hidden is the first chunk's H2D copy and the last
+// chunk's D2H copy, so the plan is [small, large, small]: an eighth of the batch at either end, the rest in the middle
+// (one large launch keeps the stream-K grid efficient).
 static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad) {
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   THY_TRY(require_device());
@@ -88,13 +91,28 @@ static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* o
   THY_TRY(m->ws.logp.reserve((size_t)B));
   if (out_grad) THY_TRY(m->ws.grad.reserve(nx));
   cudaStream_t s = m->stream;
-  static const int max_chunks = [] {   // THY_HOST_CHUNKS=1 disables the copy/compute overlap (diagnostics)
+  static const int chunk_mode = [] {   // THY_HOST_CHUNKS: 1 = no overlap, 2..8 = that many equal chunks, unset = edge plan
     const char* e = std::getenv("THY_HOST_CHUNKS");
-    const int v = e ? std::atoi(e) : 2;
-    return v < 1 ? 1 : (v > 8 ? 8 : v);
+    const int v = e ? std::atoi(e) : 0;
+    return v < 0 ? 0 : (v > 8 ? 8 : v);
   }();
-  int nch = (int)(B / 1024);
-  if (nch > max_chunks) nch = max_chunks;
+  // chunk boundaries in whole 64-chain tiles
+  int64_t bounds[9];
+  int nch = 1;
+  bounds[0] = 0;
+  if (chunk_mode == 0) {
+    if (B >= 2048) {
+      const int64_t edge = std::max<int64_t>(256, (B / 8 + 63) / 64 * 64);
+      bounds[1] = edge;
+      bounds[2] = B - edge;
+      nch = 3;
+    }
+  } else if (chunk_mode >= 2 && B / 1024 >= 2) {
+    nch = (int)std::min<int64_t>(chunk_mode, B / 1024);
+    const int64_t per = ((B + nch - 1) / nch + 63) / 64 * 64;
+    for (int k = 1; k < nch; ++k) bounds[k] = std::min<int64_t>(B, per * k);
+  }
+  bounds[nch] = B;
   if (nch < 2) {
     THY_CUDA_CHECK(cudaMemcpyAsync(m->ws.X.ptr, X, nx * sizeof(double), cudaMemcpyHostToDevice, s));
     THY_TRY(eval_batch_dev(m, B, m->ws.X.ptr, m->ws.logp.ptr, out_grad ? m->ws.grad.ptr : nullptr, false));
@@ -104,16 +122,19 @@ static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* o
     return THY_OK;
   }
   THY_TRY(ensure_copy_streams(m));
-  const int64_t per = ((B + nch - 1) / nch + 63) / 64 * 64;   // whole 64-chain tiles per chunk
   // the copy streams must not start before earlier work on the model's stream has finished with the staging buffers
   THY_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
   THY_CUDA_CHECK(cudaStreamWaitEvent(m->h2d_stream, m->ev_start, 0));
-  int k = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
-    const int64_t nb = (B - b0 < per) ? (B - b0) : per;
+  // all input copies are queued up front (they serialise on the H2D stream), so the copy engine never waits for the host
+  for (int k = 0; k < nch; ++k) {
+    const int64_t b0 = bounds[k], nb = bounds[k + 1] - bounds[k];
     const size_t off = (size_t)b0 * m->d, cnt = (size_t)nb * m->d;
     THY_CUDA_CHECK(cudaMemcpyAsync(m->ws.X.ptr + off, X + off, cnt * sizeof(double), cudaMemcpyHostToDevice, m->h2d_stream));
     THY_CUDA_CHECK(cudaEventRecord(m->ev_h2d[k], m->h2d_stream));
+  }
+  for (int k = 0; k < nch; ++k) {
+    const int64_t b0 = bounds[k], nb = bounds[k + 1] - bounds[k];
+    const size_t off = (size_t)b0 * m->d, cnt = (size_t)nb * m->d;
     THY_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_h2d[k], 0));
     THY_TRY(eval_batch_dev(m, nb, m->ws.X.ptr + off, m->ws.logp.ptr + b0, out_grad ? m->ws.grad.ptr + off : nullptr, false));
     THY_CUDA_CHECK(cudaEventRecord(m->ev_done[k], s));
