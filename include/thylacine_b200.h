@@ -122,7 +122,12 @@ typedef enum thy_option {
   /* Kernel selection for linear-Gaussian terms: 0 = auto, 1 = force generic tiled kernels,
    * 2 = force fused DMMA kernel (error if the shape is unsupported), 3 = force streaming (small-batch) kernel,
    * 4 = force the wide DMMA GEMM pair (any width / link; not for uniform observations or FD Jacobians).      */
-  THY_OPT_KERNEL_PATH = 2
+  THY_OPT_KERNEL_PATH = 2,
+  /* When a posterior is one linear term over the whole parameter vector with per-coordinate priors, the fused DMMA
+   * kernel can evaluate the priors in its output step (one launch per evaluation, no read-modify-write of the
+   * outputs): 0 = never, 1 (default) = when the cost model says the saved prior pass outweighs the slower output
+   * step (small terms, e.g. a collapsed posterior), 2 = always.                                                  */
+  THY_OPT_FUSE_PRIOR = 3
 } thy_option;
 thy_status thy_model_set_option(thy_model_t m, int option, int value);
 

@@ -434,3 +434,52 @@ def test_wide_path_cauchy_links_multi_label_offset(link, faithful):
     for b in range(0, B, 7):
         assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
         assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+# ---- single-kernel evaluation: priors folded into the fused kernel's output step -------------------------------------
+@pytest.mark.parametrize("B", [1, 63, 64, 700, 4096])
+def test_fused_prior_single_kernel_matches_the_separate_prior_kernel_and_the_oracle(B):
+    import torch
+    rng = np.random.default_rng(B)
+    da, db, n = 5, 9, 300
+    A = {"a": rng.standard_normal((n, da)), "b": rng.standard_normal((n, db))}
+    y = rng.standard_normal(n)
+    ci = rng.uniform(0.2, 1.0, n)
+    priors = [t.UniformPrior.fromBounds("a", np.full(da, 2.0), np.full(da, -2.0)),
+              t.GaussianPrior.fromConfidenceIntervals("b", rng.standard_normal(db), rng.uniform(1, 3, db))]
+    lik = [t.GaussianLikelihood(t.LinearForwardModel.of(transform=A), y, ci)]
+    X = rng.uniform(-1.9, 1.9, (B, da + db))
+    X[B // 2, 2] = 2.0                                                         # on the open upper bound: outside
+    outs = []
+    for fuse in (True, False):
+        post = t.UnnormalisedPosterior(priors, lik, kernelPath=capi.KERNEL_FUSED_DMMA, fusePrior=2 if fuse else 0)
+        launches0 = t.kernelLaunchCount()
+        lp, g = post.logPdfGradBatch(X)                                        # pageable numpy buffers: staged copies
+        launches = t.kernelLaunchCount() - launches0
+        assert launches == (1 if fuse else 2) * (1 if B < 2048 else 3)
+        xp = torch.from_numpy(X).pin_memory()                                  # pinned buffers: the same chunk plan
+        lpp, gp = torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, da + db, dtype=torch.float64).pin_memory()
+        import ctypes
+        dp = ctypes.POINTER(ctypes.c_double)
+        capi.check(t.lib().thy_logpdf_grad_batch(post.handle, B, ctypes.cast(xp.data_ptr(), dp), ctypes.cast(lpp.data_ptr(), dp),
+                                                 ctypes.cast(gp.data_ptr(), dp)))
+        assert np.array_equal(lpp.numpy(), lp) and np.array_equal(gp.numpy(), g)
+        lv = post.logPdfBatch(X)                                               # value only
+        assert np.array_equal(lv, lp)
+        outs.append((lp, g))
+        post.close()
+    (lf, gf), (ls, gs) = outs
+    assert lf[B // 2] == -math.inf and ls[B // 2] == -math.inf
+    ok = np.isfinite(ls)
+    assert np.max(np.abs(lf[ok] - ls[ok]) / np.maximum(1.0, np.abs(ls[ok]))) < 1e-13 if ok.any() else True
+    assert rel_err_grad(gf, gs) < 1e-13
+    ref = o.Posterior([o.uniform_prior_from_bounds("a", np.full(da, 2.0), np.full(da, -2.0)),
+                       o.gaussian_prior_from_ci("b", priors[1].a, priors[1].b)],
+                      [o.gaussian_likelihood(o.LinearForwardModel(A), y, ci)])
+    for b in range(0, B, max(1, B // 7)):
+        want = ref.log_pdf(X[b])
+        if math.isinf(want):
+            assert lf[b] == -math.inf
+        else:
+            assert lf[b] == pytest.approx(want, rel=TOL)
+        assert rel_err_grad(gf[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL

@@ -22,7 +22,7 @@ THY_ERR_STATE, THY_ERR_UNSUPPORTED, THY_ERR_NO_DEVICE = 5, 6, 7
 DIST_GAUSSIAN, DIST_CAUCHY, DIST_UNIFORM = 0, 1, 2
 LINK_IDENTITY, LINK_TANH, LINK_EXP, LINK_SQUARE, LINK_SOFTPLUS, LINK_SIGMOID = range(6)
 JAC_CONSTANT, JAC_ANALYTIC, JAC_FINITE_DIFFERENCE = 0, 1, 2
-OPT_CAUCHY_REFERENCE_SIGN, OPT_FD_INCREMENTAL, OPT_KERNEL_PATH = 0, 1, 2
+OPT_CAUCHY_REFERENCE_SIGN, OPT_FD_INCREMENTAL, OPT_KERNEL_PATH, OPT_FUSE_PRIOR = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED_DMMA, KERNEL_STREAM, KERNEL_WIDE = 0, 1, 2, 3, 4
 
 

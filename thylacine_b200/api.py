@@ -199,7 +199,8 @@ class UnnormalisedPosterior:
     """
 
     def __init__(self, priors: Sequence[_PriorSpec], likelihoods: Sequence[_LikelihoodSpec] = (),
-                 cauchyReferenceSign: bool = True, fdIncremental: bool = False, kernelPath: int = _capi.KERNEL_AUTO):
+                 cauchyReferenceSign: bool = True, fdIncremental: bool = False, kernelPath: int = _capi.KERNEL_AUTO,
+                 fusePrior: int = 1):
         L = lib()
         self._lib = L
         h = C.c_void_p()
@@ -223,6 +224,7 @@ class UnnormalisedPosterior:
             check(L.thy_model_set_option(h, _capi.OPT_CAUCHY_REFERENCE_SIGN, 1 if cauchyReferenceSign else 0))
             check(L.thy_model_set_option(h, _capi.OPT_FD_INCREMENTAL, 1 if fdIncremental else 0))
             check(L.thy_model_set_option(h, _capi.OPT_KERNEL_PATH, int(kernelPath)))
+            check(L.thy_model_set_option(h, _capi.OPT_FUSE_PRIOR, int(fusePrior)))
             check(L.thy_model_finalize(h))
             d = C.c_int()
             check(L.thy_model_dimension(h, C.byref(d)))

@@ -154,6 +154,7 @@ thy_status thy_model_collapse(thy_model_t m, thy_model_t* out) {
   c->priors = m->priors;
   c->opt_cauchy_ref_sign = m->opt_cauchy_ref_sign;
   c->opt_fd_incremental = m->opt_fd_incremental;
+  c->opt_fuse_prior = m->opt_fuse_prior;
   c->opt_kernel_path = m->opt_kernel_path == 4 ? 0 : m->opt_kernel_path;
   c->stream = (m->stream == m->own_stream) ? (cudaStream_t)0 : m->stream;   // an external stream is shared; an owned one is not
   std::vector<double> ones(du, 1.0);

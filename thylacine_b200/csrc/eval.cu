@@ -7,45 +7,76 @@
 
 namespace thy {
 
-// One likelihood term added into logp / grad: kernel-path selection lives here.
-thy_status launch_likelihood(thy_model_s* m, LikDevOwner& owner, int64_t B, const double* X, double* logp, double* grad,
-                             double csign, cudaStream_t s) {
-  LikDevOwner* own = &owner;
-  const LikDev& lk = own->view;
+// Kernel path of one likelihood term for a batch of B points (0 = not resolvable: status set).
+static int select_path(thy_model_s* m, const LikDev& lk, int64_t B, bool want_grad, thy_status* st) {
+  *st = THY_OK;
   const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&
                        lk.distribution != THY_DIST_UNIFORM);
   int path = m->opt_kernel_path;
-  if (path == 2 && !(linear && fused_dmma_supported(lk, grad != nullptr)))
-    return fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
-  if (path == 3 && !(linear && stream_supported(lk, B)))
-    return fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
-  if (path == 4 && !wide_supported(lk))
-    return fail(THY_ERR_UNSUPPORTED, "wide DMMA path does not support this likelihood (uniform observations / FD Jacobian)");
+  if (path == 2 && !(linear && fused_dmma_supported(lk, want_grad))) {
+    *st = fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
+    return 0;
+  }
+  if (path == 3 && !(linear && stream_supported(lk, B))) {
+    *st = fail(THY_ERR_UNSUPPORTED, "streaming kernel does not support this likelihood shape / batch");
+    return 0;
+  }
+  if (path == 4 && !wide_supported(lk)) {
+    *st = fail(THY_ERR_UNSUPPORTED, "wide DMMA path does not support this likelihood (uniform observations / FD Jacobian)");
+    return 0;
+  }
   if (path == 0) {
     if (linear && stream_supported(lk, B) &&
-        (!fused_dmma_supported(lk, grad != nullptr) || stream_cost_model(lk, B) <= fused_cost_model(lk, B)))
+        (!fused_dmma_supported(lk, want_grad) || stream_cost_model(lk, B) <= fused_cost_model(lk, B)))
       path = 3;
-    else if (linear && fused_dmma_supported(lk, grad != nullptr))
+    else if (linear && fused_dmma_supported(lk, want_grad))
       path = 2;
     else if (wide_supported(lk) && B >= 32 && (long long)lk.n * lk.dl >= 4096)
       path = 4;
     else
       path = 1;
   }
+  return path;
+}
+
+// One likelihood term added into logp / grad (fuse_prior: the fused kernel also evaluates the priors and writes).
+thy_status launch_likelihood(thy_model_s* m, LikDevOwner& owner, int64_t B, const double* X, double* logp, double* grad,
+                             double csign, cudaStream_t s, bool fuse_prior) {
+  thy_status st = THY_OK;
+  const int path = select_path(m, owner.view, B, grad != nullptr, &st);
+  THY_TRY(st);
+  if (fuse_prior && path != 2) return fail(THY_ERR_STATE, "fused priors need the fused DMMA path");
   if (path == 2) {
     m->last_path = "fused_dmma";
-    THY_TRY(launch_fused_dmma(m, *own, B, X, logp, grad, csign, s));
+    THY_TRY(launch_fused_dmma(m, owner, B, X, logp, grad, csign, s, fuse_prior));
   } else if (path == 3) {
     m->last_path = "stream";
-    THY_TRY(launch_stream(m, *own, B, X, logp, grad, csign, s));
+    THY_TRY(launch_stream(m, owner, B, X, logp, grad, csign, s));
   } else if (path == 4) {
     m->last_path = "wide_dmma";
-    THY_TRY(launch_wide_likelihood(m, *own, B, X, logp, grad, csign, s));
+    THY_TRY(launch_wide_likelihood(m, owner, B, X, logp, grad, csign, s));
   } else {
     m->last_path = "generic";
-    THY_TRY(launch_generic_likelihood(m, *own, B, X, logp, grad, csign, s));
+    THY_TRY(launch_generic_likelihood(m, owner, B, X, logp, grad, csign, s));
   }
   return THY_OK;
+}
+
+// True when a whole evaluation of B points should be ONE kernel: the fused DMMA kernel with the priors folded into its
+// output step.  Measured on B200: the folded output step costs the fused kernel ~3 % (config 2: 543 -> 561 us) and saves
+// the prior kernel (a launch plus one pass over X and the outputs), so it pays for small terms -- the collapsed
+// posterior gains 18-27 % -- and not for config 2.  opt_fuse_prior: 0 never, 1 by this cost model, 2 always.
+// (Writing the outputs straight into pinned host memory from the same kernel was tried and dropped: its scattered
+// 8-byte reads and writes across PCIe halved the end-to-end rate.)
+static bool single_kernel_eval(thy_model_s* m, int64_t B, bool want_grad) {
+  if (m->lik_dev.size() != 1 || !m->opt_fuse_prior) return false;
+  LikDevOwner& own = *m->lik_dev[0];
+  if (!fused_prior_supported(m, own)) return false;
+  thy_status st = THY_OK;
+  if (select_path(m, own.view, B, want_grad, &st) != 2) return false;
+  if (m->opt_fuse_prior >= 2) return true;
+  const double t_prior = 5e-6 + (double)B * m->d * 24.0 / 6e12;
+  return 0.03 * fused_cost_model(own.view, B) < t_prior;
 }
 
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign,
@@ -56,9 +87,11 @@ thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* lo
   if (!X || !logp) return fail(THY_ERR_INVALID_ARGUMENT, "null device pointer");
   const double csign = (cauchy_correct_sign || !m->opt_cauchy_ref_sign) ? -1.0 : 1.0;
   cudaStream_t s = m->stream;
+  if (!likelihoods_only && single_kernel_eval(m, B, grad != nullptr))
+    return launch_likelihood(m, *m->lik_dev[0], B, X, logp, grad, csign, s, true);
   // likelihoods_only: logp (and grad) are already initialised by the caller; only the likelihood terms are added
   if (!likelihoods_only) THY_TRY(launch_prior(m->prior_view, B, X, logp, grad, csign, s));
-  for (auto& own : m->lik_dev) THY_TRY(launch_likelihood(m, *own, B, X, logp, grad, csign, s));
+  for (auto& own : m->lik_dev) THY_TRY(launch_likelihood(m, *own, B, X, logp, grad, csign, s, false));
   if (m->lik_dev.empty()) m->last_path = "priors_only";
   return THY_OK;
 }
@@ -87,10 +120,10 @@ static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* o
   if (B == 0) return THY_OK;
   if (!X || !out_logp) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
   const size_t nx = (size_t)B * m->d;
+  cudaStream_t s = m->stream;
   THY_TRY(m->ws.X.reserve(nx));
   THY_TRY(m->ws.logp.reserve((size_t)B));
   if (out_grad) THY_TRY(m->ws.grad.reserve(nx));
-  cudaStream_t s = m->stream;
   static const int chunk_mode = [] {   // THY_HOST_CHUNKS: 1 = no overlap, 2..8 = that many equal chunks, unset = edge plan
     const char* e = std::getenv("THY_HOST_CHUNKS");
     const int v = e ? std::atoi(e) : 0;

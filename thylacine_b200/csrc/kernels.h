@@ -16,8 +16,11 @@ thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int
 int fused_nt_for(int dl);  // 0 when the width is not covered by the fused kernel
 bool fused_dmma_supported(const LikDev& lik, bool want_grad);
 double fused_cost_model(const LikDev& lik, int64_t B);    // seconds, for auto-selection
+// fuse_prior: the kernel also evaluates the per-coordinate priors and WRITES logp / grad (single term over the whole
+// flat vector, no Cauchy / full-covariance prior blocks: fused_prior_supported)
+bool fused_prior_supported(const thy_model_s* m, const LikDevOwner& lik);
 thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
-                             double cauchy_sign, cudaStream_t s);
+                             double cauchy_sign, cudaStream_t s, bool fuse_prior = false);
 
 // kernels_stream.cu -- small-batch memory-bound pass (A streamed once per batch)
 bool stream_supported(const LikDev& lik, int64_t B);

@@ -51,6 +51,13 @@ struct FusedParams {
   int stages;
   int distribution;
   double log_const, cauchy_sign;
+  // fuse_prior: the per-coordinate priors of the same coordinates are evaluated in the output step and the kernel
+  // WRITES logp / grad (no prior kernel, no read-modify-write: the outputs may then live in pinned host memory)
+  int fuse_prior;
+  const int* pr_kind;
+  const double* pr_p0;
+  const double* pr_p1;
+  double pr_log_const;
 };
 
 template <int NT>
@@ -72,10 +79,51 @@ __device__ __forceinline__ double apply_scale(int distribution, double q, int n,
   return -cauchy_sign * (1.0 + n) / (1.0 + q);
 }
 
+// Output of one chain row with the per-coordinate priors folded in (lane (g, q) of the owning warp holds columns
+// 8t + 2q, 8t + 2q + 1 of the gradient).  Every lane of the warp must call this (quad shuffles inside); rows beyond the
+// batch are masked by `live`.  The kernel WRITES logp / grad here instead of adding to what the prior kernel left.
+template <int NT, bool WANT_GRAD>
+__device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long long chain, bool live, int q4, double qsum,
+                                                     const double (&ga)[WANT_GRAD ? NT : 1][2]) {
+  const double lik = apply_logp(p.distribution, qsum, p.n, p.log_const);
+  const double sc = WANT_GRAD ? apply_scale(p.distribution, qsum, p.n, p.cauchy_sign) : 0.0;
+  // fused priors (the term reads the whole flat vector in order: column j IS coordinate j)
+  const double* xrow = p.X + chain * p.d;
+  double* grow = WANT_GRAD ? p.grad + chain * p.d : nullptr;
+  double acc = 0.0;
+  bool inside = true;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 8 * t + 2 * q4 + h;
+      if (live && j < p.dl) {
+        const int kind = p.pr_kind[j];
+        const double xv = xrow[j];
+        double gj = 0.0;
+        if (kind == PK_GAUSS_DIAG) {
+          const double dl = p.pr_p0[j] - xv;
+          const double w = dl * p.pr_p1[j];
+          acc += dl * w;
+          gj = w;
+        } else if (kind == PK_UNIFORM) {
+          inside = inside && (xv >= p.pr_p0[j]) && (xv < p.pr_p1[j]);
+        }
+        if (WANT_GRAD) grow[j] = gj + sc * ga[WANT_GRAD ? t : 0][h];
+      }
+    }
+  }
+  acc = quad_sum(acc);
+  const unsigned ballot = __ballot_sync(0xffffffffu, inside);
+  const int lane = threadIdx.x & 31;
+  const bool inside_all = ((ballot >> (lane & ~3)) & 0xFu) == 0xFu;
+  if (live && q4 == 0) p.logp[chain] = (inside_all ? (-0.5 * acc + p.pr_log_const) : -INFINITY) + lik;
+}
+
 // Stream-K combine.  The last warp to deliver its segment of a (tile, warp) row group sums all segments, always in CTA
 // order, so the result does not depend on which CTA happens to finish last (run-to-run bit-identical).  Kept out of
 // line: it runs at most twice per CTA and must not cost the main loop any registers.
-template <int NT, bool WANT_GRAD>
+template <int NT, bool WANT_GRAD, bool FUSE_PRIOR>
 __device__ __noinline__ void combine_segments(const FusedParams& p, long long tile, int warp, int lane, long long G) {
   using C = Cfg<NT>;
   const int g8 = lane >> 2, q4 = lane & 3;
@@ -118,7 +166,9 @@ __device__ __noinline__ void combine_segments(const FusedParams& p, long long ti
       }
     }
   }
-  if (chain < p.B) {
+  if (FUSE_PRIOR) {
+    emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qtot, gs);
+  } else if (chain < p.B) {
     if (q4 == 0) p.logp[chain] += apply_logp(p.distribution, qtot, p.n, p.log_const);
     if (WANT_GRAD) {
       const double sc = apply_scale(p.distribution, qtot, p.n, p.cauchy_sign);
@@ -134,7 +184,7 @@ __device__ __noinline__ void combine_segments(const FusedParams& p, long long ti
   if (lane == 0) p.tickets[tile * NW + warp] = 0u;   // re-arm for the next launch
 }
 
-template <int NT, bool WANT_GRAD>
+template <int NT, bool WANT_GRAD, bool FUSE_PRIOR>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedParams p) {
   using C = Cfg<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -203,7 +253,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedPara
     const long long chain = tile * TILE_B + warp * 8 + g8;
     const bool full_tile = (ue - ub) == p.nblk;
     if (full_tile) {
-      if (chain < p.B) {
+      if (FUSE_PRIOR) {
+        emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qsum, ga);
+      } else if (chain < p.B) {
         if (q4 == 0) p.logp[chain] += apply_logp(p.distribution, qsum, p.n, p.log_const);
         if (WANT_GRAD) {
           const double sc = apply_scale(p.distribution, qsum, p.n, p.cauchy_sign);
@@ -227,7 +279,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedPara
         for (int t = 0; t < NT; ++t)
           *reinterpret_cast<double2*>(prow + 8 * t + 2 * q4) = make_double2(ga[WANT_GRAD ? t : 0][0], ga[WANT_GRAD ? t : 0][1]);
       }
-      combine_segments<NT, WANT_GRAD>(p, tile, warp, lane, G);
+      combine_segments<NT, WANT_GRAD, FUSE_PRIOR>(p, tile, warp, lane, G);
     }
   };
 
@@ -326,12 +378,15 @@ thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_
   }
   p.tickets = m->ws.fused_tickets.ptr;
   KernelTimer timer(m, s);
-  if (want_grad) {
-    THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fused_dmma<NT, true><<<G, (NW + 1) * 32, smem, s>>>(p);
+  auto launch = [&](auto kernel) -> thy_status {
+    THY_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<G, (NW + 1) * 32, smem, s>>>(p);
+    return THY_OK;
+  };
+  if (p.fuse_prior) {
+    THY_TRY(want_grad ? launch(k_fused_dmma<NT, true, true>) : launch(k_fused_dmma<NT, false, true>));
   } else {
-    THY_CUDA_CHECK(cudaFuncSetAttribute(k_fused_dmma<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fused_dmma<NT, false><<<G, (NW + 1) * 32, smem, s>>>(p);
+    THY_TRY(want_grad ? launch(k_fused_dmma<NT, true, false>) : launch(k_fused_dmma<NT, false, false>));
   }
   timer.stop();
   count_launch();
@@ -361,10 +416,23 @@ double fused_cost_model(const LikDev& lik, int64_t B) {
   return 5e-6 + (t > 6e-6 ? t : 6e-6);
 }
 
+bool fused_prior_supported(const thy_model_s* m, const LikDevOwner& lik) {
+  return m->lik_dev.size() == 1 && m->prior_view.n_special == 0 && lik.view.dl == m->d && lik.contiguous &&
+         !lik.col_host.empty() && lik.col_host[0] == 0;
+}
+
 thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
-                             double cauchy_sign, cudaStream_t s) {
+                             double cauchy_sign, cudaStream_t s, bool fuse_prior) {
   const LikDev& lk = lik.view;
   FusedParams p{};
+  if (fuse_prior) {
+    if (!fused_prior_supported(m, lik)) return fail(THY_ERR_STATE, "fused priors requested for an unsupported model");
+    p.fuse_prior = 1;
+    p.pr_kind = m->prior_view.kind;
+    p.pr_p0 = m->prior_view.p0;
+    p.pr_p1 = m->prior_view.p1;
+    p.pr_log_const = m->prior_view.log_const;
+  }
   p.A = lk.A;
   p.yiv = lk.yiv_lin;
   p.col = lk.col;

@@ -350,6 +350,10 @@ thy_status thy_model_set_option(thy_model_t m, int option, int value) {
       if (value < 0 || value > 4) return fail(THY_ERR_INVALID_ARGUMENT, "kernel path must be 0..4");
       m->opt_kernel_path = value;
       return THY_OK;
+    case THY_OPT_FUSE_PRIOR:
+      if (value < 0 || value > 2) return fail(THY_ERR_INVALID_ARGUMENT, "fuse-prior option must be 0, 1 or 2");
+      m->opt_fuse_prior = value;
+      return THY_OK;
     default: return fail(THY_ERR_INVALID_ARGUMENT, "unknown option");
   }
 }

@@ -101,6 +101,7 @@ struct thy_model_s {
   int opt_cauchy_ref_sign = 1;
   int opt_fd_incremental = 0;
   int opt_kernel_path = 0;
+  int opt_fuse_prior = 1;
   cudaStream_t stream = 0;
   // Default stream of the handle, created at finalize: a BLOCKING stream, so it keeps the implicit ordering with the
   // legacy default stream that callers of the *_dev entry points rely on, yet (unlike stream 0) it can be captured
@@ -154,7 +155,7 @@ struct KernelTimer {
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false,
                           bool likelihoods_only = false);
 thy_status launch_likelihood(thy_model_s* m, LikDevOwner& owner, int64_t B, const double* X, double* logp, double* grad,
-                             double csign, cudaStream_t s);
+                             double csign, cudaStream_t s, bool fuse_prior = false);
 // model.cu
 thy_status build_lik_dev(thy_model_s* m, int distribution, int link, int jacobian, double differential, int n,
                          const std::vector<int>& cols, const std::vector<const double*>& blocks,
