@@ -117,7 +117,9 @@ typedef enum thy_option {
    * 0 = mathematically correct sign.  Samplers built on a model always use the correct sign.             */
   THY_OPT_CAUCHY_REFERENCE_SIGN = 0,
   /* Finite-difference evaluation: 0 (default) = every perturbed point theta + h e_j goes through the full
-   * forward model (the reference's arithmetic); 1 = incremental z + h A[:,j] (same limit, fewer flops).   */
+   * forward model (the reference's arithmetic; the perturbed dot products reuse the unperturbed prefix sums, which
+   * is the same rounding sequence); 1 = incremental z + h A[:,j] (same limit, fewer flops); 2 = as 0 with every
+   * perturbed dot product recomputed from its first term (diagnostics: bit-identical to 0, ~10x slower).         */
   THY_OPT_FD_INCREMENTAL = 1,
   /* Kernel selection for linear-Gaussian terms: 0 = auto, 1 = force generic tiled kernels,
    * 2 = force fused DMMA kernel (error if the shape is unsupported), 3 = force streaming (small-batch) kernel,

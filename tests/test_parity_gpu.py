@@ -483,3 +483,23 @@ def test_fused_prior_single_kernel_matches_the_separate_prior_kernel_and_the_ora
         else:
             assert lf[b] == pytest.approx(want, rel=TOL)
         assert rel_err_grad(gf[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+@pytest.mark.parametrize("d,n,B", [(20, 64, 16), (200, 256, 96), (7, 5, 3), (131, 70, 40)])
+def test_fd_literal_prefix_kernel_is_bit_identical_to_the_plain_literal_kernel(d, n, B):
+    """The perturbed dot products start from the unperturbed prefix sums (k_fd_adjoint_prefix): the same fma sequence,
+    so the gradient must equal the plain literal kernel's BIT FOR BIT (fdIncremental=2 selects the plain kernel)."""
+    rng = np.random.default_rng(d + n)
+    A = rng.standard_normal((n, d)) / np.sqrt(d)
+    off = 0.1 * rng.standard_normal(n)
+    y = np.tanh(A @ rng.standard_normal(d) + off) + 0.05 * rng.standard_normal(n)
+    X = 0.5 * rng.standard_normal((B, d))
+    outs = []
+    for mode in (0, 2):
+        fm = t.NonLinearForwardModel.of("tanh", {"w": A}, differential=1e-6, vectorOffset=off)
+        post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", np.zeros(d), np.full(d, 4.0))],
+                                       [t.CauchyLikelihood(fm, y, np.full(n, 0.1))], cauchyReferenceSign=False, fdIncremental=mode)
+        outs.append(post.logPdfGradBatch(X))
+        post.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.all(np.isfinite(outs[0][1])) and np.max(np.abs(outs[0][1])) > 0

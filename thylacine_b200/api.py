@@ -222,7 +222,7 @@ class UnnormalisedPosterior:
             for lk in likelihoods:
                 self._add_likelihood(lk)
             check(L.thy_model_set_option(h, _capi.OPT_CAUCHY_REFERENCE_SIGN, 1 if cauchyReferenceSign else 0))
-            check(L.thy_model_set_option(h, _capi.OPT_FD_INCREMENTAL, 1 if fdIncremental else 0))
+            check(L.thy_model_set_option(h, _capi.OPT_FD_INCREMENTAL, int(fdIncremental)))
             check(L.thy_model_set_option(h, _capi.OPT_KERNEL_PATH, int(kernelPath)))
             check(L.thy_model_set_option(h, _capi.OPT_FUSE_PRIOR, int(fusePrior)))
             check(L.thy_model_finalize(h))

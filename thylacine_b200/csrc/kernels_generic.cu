@@ -244,6 +244,130 @@ __global__ void __launch_bounds__(128) k_fd_adjoint(LikDev lk, int d, long long 
   if (active) grad[b * d + lk.col[j]] += scale[b] * acc;
 }
 
+// Literal finite differences without the redundant work.  The reference evaluates every perturbed model as a full
+// forward map; for f = link(A theta + offset) that is, per observation row, the dot product sum_k a_k theta^(j)_k with
+// theta^(j) = theta + h e_j.  Accumulated in k order (one fma chain), every term before k = j is the SAME rounding
+// sequence as the unperturbed dot product, so the perturbed chain can start from the unperturbed PREFIX P_j and only
+// run k = j .. dl-1: bit-for-bit the value of the full chain (and of k_fd_adjoint's literal branch), for dl^2 / 2
+// instead of 2 dl^2 fused multiply-adds per row.
+// Mapping: a tile of 32 observation rows sits in shared memory with its prefix arrays; lane = row, and a warp walks
+// one block of FDP_J perturbed columns at a time, so every a_k / theta_k read feeds FDP_J chains (register blocking: the
+// plain mapping was shared-memory bound) and all lanes of a warp have the same trip count.  Column blocks are taken in
+// (q, last - q) pairs so every warp does the same number of chain steps.  The Jacobian entries overwrite the prefix
+// slots they started from; a last pass adds w_i J_ij over the rows in ascending order (the plain kernel's order).
+constexpr int FDP_J = 8;
+
+__device__ __forceinline__ void fdp_block(const LikDev& lk, int dl, int pitch, int j0, int r, bool row_live,
+                                          const double* __restrict__ theta, const double* __restrict__ At,
+                                          double* __restrict__ P, double h, double inv_h, double f0r, double offr) {
+  const double* a = At + (size_t)r * pitch;
+  double* pr = P + (size_t)r * pitch;
+  double s[FDP_J];
+#pragma unroll
+  for (int u = 0; u < FDP_J; ++u) s[u] = 0.0;
+  // triangular start: chain u begins at k = j0 + u with the nudged coordinate on top of the unperturbed prefix
+#pragma unroll
+  for (int kk = 0; kk < FDP_J; ++kk) {
+    const int k = j0 + kk;
+    if (k < dl) {
+      const double ak = a[k], th = theta[k];
+#pragma unroll
+      for (int u = 0; u < FDP_J; ++u) {
+        if (u == kk) s[u] = fma(ak, th + h, pr[k]);
+        else if (u < kk) s[u] = fma(ak, th, s[u]);
+      }
+    }
+  }
+#pragma unroll 4
+  for (int k = j0 + FDP_J; k < dl; ++k) {
+    const double ak = a[k], th = theta[k];
+#pragma unroll
+    for (int u = 0; u < FDP_J; ++u) s[u] = fma(ak, th, s[u]);
+  }
+  if (row_live) {
+#pragma unroll
+    for (int u = 0; u < FDP_J; ++u)
+      if (j0 + u < dl) pr[j0 + u] = (link_eval(lk.link, s[u] + offr) - f0r) * inv_h;
+  }
+}
+
+__global__ void __launch_bounds__(128, 2) k_fd_adjoint_prefix(LikDev lk, int d, long long B, const double* __restrict__ X,
+                                                           const double* __restrict__ W, const double* __restrict__ scale,
+                                                           double* __restrict__ grad) {
+  extern __shared__ double sh[];
+  constexpr int ROWS = 32;
+  const int dl = lk.dl, pitch = dl + 1 + ((dl & 1) ? 0 : 1);   // odd pitch: lanes walking one column hit distinct banks
+  double* theta = sh;
+  double* At = theta + dl;                 // [ROWS][pitch]
+  double* P = At + (size_t)ROWS * pitch;   // [ROWS][pitch]: prefix sums, overwritten by the Jacobian entries
+  double* f0 = P + (size_t)ROWS * pitch;   // [ROWS]
+  double* ws = f0 + ROWS;                  // [ROWS]
+  double* os = ws + ROWS;                  // [ROWS]
+  const long long b = blockIdx.x;
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int k = threadIdx.x; k < dl; k += blockDim.x) theta[k] = X[b * d + lk.col[k]];
+  const double h = lk.differential, inv_h = 1 / h;
+  const int nblk = (dl + FDP_J - 1) / FDP_J;
+  const int npair = (nblk + 1) / 2;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};    // columns threadIdx.x + 128 m (dl <= 512)
+  for (int i0 = 0; i0 < lk.n; i0 += ROWS) {
+    const int ni = (lk.n - i0 < ROWS) ? (lk.n - i0) : ROWS;
+    __syncthreads();
+    for (int r = warp; r < ROWS; r += nwarps) {   // a warp copies whole rows: coalesced, no index division
+      const double* src = lk.A + (size_t)(i0 + r) * lk.lds;
+      double* dst = At + (size_t)r * pitch;
+      for (int k = lane; k < dl; k += 32) dst[k] = (r < ni) ? src[k] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {   // unperturbed chain and its prefixes, one row per lane
+      const double* a = At + (size_t)lane * pitch;
+      double* pr = P + (size_t)lane * pitch;
+      double s0 = 0.0;
+      for (int k = 0; k < dl; ++k) {
+        pr[k] = s0;
+        s0 = fma(a[k], theta[k], s0);
+      }
+      const bool live = lane < ni;
+      const double off = live ? lk.off[i0 + lane] : 0.0;
+      os[lane] = off;
+      f0[lane] = link_eval(lk.link, s0 + off);
+      ws[lane] = live ? W[b * lk.n_pad + i0 + lane] : 0.0;
+    }
+    __syncthreads();
+    const double f0r = f0[lane], offr = os[lane];
+    const bool row_live = lane < ni;
+    for (int q = warp; q < npair; q += nwarps) {
+      fdp_block(lk, dl, pitch, q * FDP_J, lane, row_live, theta, At, P, h, inv_h, f0r, offr);
+      const int q2 = nblk - 1 - q;
+      if (q2 != q) fdp_block(lk, dl, pitch, q2 * FDP_J, lane, row_live, theta, At, P, h, inv_h, f0r, offr);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mth = 0; mth < 4; ++mth) {
+      const int j = threadIdx.x + 128 * mth;
+      if (j < dl) {
+        double a2 = acc[mth];
+        for (int r = 0; r < ni; ++r) a2 = fma(ws[r], P[(size_t)r * pitch + j], a2);   // ascending rows
+        acc[mth] = a2;
+      }
+    }
+  }
+#pragma unroll
+  for (int mth = 0; mth < 4; ++mth) {
+    const int j = threadIdx.x + 128 * mth;
+    if (j < dl) grad[b * d + lk.col[j]] += scale[b] * acc[mth];
+  }
+}
+
+// shared memory of k_fd_adjoint_prefix (0: the width is outside its scope, use the plain kernel)
+static size_t fd_prefix_smem(int dl) {
+  if (dl > 512) return 0;
+  const size_t pitch = dl + 1 + ((dl & 1) ? 0 : 1);
+  const size_t bytes = ((size_t)dl + 32 * (2 * pitch + 3)) * sizeof(double);
+  return bytes <= (size_t)110 * 1024 ? bytes : 0;
+}
+
 thy_status launch_finish_generic(const LikDev& lk, long long B, const double* partS, int n_tiles, double* logp, double* scale,
                                  double cauchy_sign, cudaStream_t s) {
   k_finish_generic<<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(lk, B, partS, n_tiles, logp, scale, cauchy_sign);
@@ -278,12 +402,20 @@ thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int
     count_launch(2);
     if (want_adj) {
       if (fd) {
+        const size_t psmem = (m->opt_fd_incremental != 0) ? 0 : fd_prefix_smem(lk.dl);
+        if (psmem > 0) {
+          THY_CUDA_CHECK(cudaFuncSetAttribute(k_fd_adjoint_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+          k_fd_adjoint_prefix<<<(unsigned)nb, 128, psmem, s>>>(lk, m->d, nb, Xc, m->ws.W.ptr, scale, grad + c0 * m->d);
+          count_launch();
+          THY_CUDA_CHECK(cudaGetLastError());
+          continue;
+        }
         dim3 ga((unsigned)nb, (unsigned)ceil_div(lk.dl, 128));
         const size_t fd_smem = (size_t)(lk.dl + 3 * FD_TI) * sizeof(double);
         if (fd_smem > 48 * 1024)
           THY_CUDA_CHECK(cudaFuncSetAttribute(k_fd_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem));
         k_fd_adjoint<<<ga, 128, fd_smem, s>>>(lk, m->d, nb, Xc, m->ws.W.ptr, m->ws.Z.ptr, scale,
-                                                            grad + c0 * m->d, m->opt_fd_incremental);
+                                                            grad + c0 * m->d, m->opt_fd_incremental == 1 ? 1 : 0);
       } else {
         dim3 ga((unsigned)ceil_div(lk.dl, GT), (unsigned)ceil_div(nb, GT));
         k_adj_generic<<<ga, 256, 0, s>>>(lk, m->d, nb, m->ws.W.ptr, scale, grad + c0 * m->d);

@@ -345,7 +345,10 @@ thy_status thy_model_set_option(thy_model_t m, int option, int value) {
   THY_TRY(check_model(m, false));
   switch (option) {
     case THY_OPT_CAUCHY_REFERENCE_SIGN: m->opt_cauchy_ref_sign = value ? 1 : 0; return THY_OK;
-    case THY_OPT_FD_INCREMENTAL: m->opt_fd_incremental = value ? 1 : 0; return THY_OK;
+    case THY_OPT_FD_INCREMENTAL:
+      if (value < 0 || value > 2) return fail(THY_ERR_INVALID_ARGUMENT, "finite-difference mode must be 0, 1 or 2");
+      m->opt_fd_incremental = value;
+      return THY_OK;
     case THY_OPT_KERNEL_PATH:
       if (value < 0 || value > 4) return fail(THY_ERR_INVALID_ARGUMENT, "kernel path must be 0..4");
       m->opt_kernel_path = value;
