@@ -432,6 +432,10 @@ def run_ours(args):
 
 
 def main():
+    # Watchdog: a stalled device call must not hold a GPU box for the rest of its lease.  After the limit the Python
+    # stacks are dumped to stderr and the process exits (works even while the main thread sits inside a C call).
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("THY_WATCHDOG_SECONDS", "1500")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

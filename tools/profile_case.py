@@ -4,6 +4,7 @@
     python tools/profile_case.py --case c2|c3|c5_analytic|c5_fd|stream|slq [--reps 3]
 """
 import argparse
+import os
 import sys
 from pathlib import Path
 
@@ -14,6 +15,10 @@ sys.path.insert(0, str(ROOT))
 
 
 def main():
+    # Watchdog: a stalled device call must not hold a GPU box for the rest of its lease.  After the limit the Python
+    # stacks are dumped to stderr and the process exits (works even while the main thread sits inside a C call).
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("THY_WATCHDOG_SECONDS", "600")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", required=True)
     ap.add_argument("--reps", type=int, default=3)

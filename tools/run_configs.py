@@ -224,6 +224,10 @@ def stream(t, torch, out, d=100, n=1_000_000):
 
 
 def main():
+    # Watchdog: a stalled device call must not hold a GPU box for the rest of its lease.  After the limit the Python
+    # stacks are dumped to stderr and the process exits (works even while the main thread sits inside a C call).
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("THY_WATCHDOG_SECONDS", "600")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="c1,c2hmc,c3,c4,c5")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "configs.json"))

@@ -28,6 +28,10 @@ sys.path.insert(0, str(ROOT / "tools"))
 
 
 def main():
+    # Watchdog: a stalled device call must not hold a GPU box for the rest of its lease.  After the limit the Python
+    # stacks are dumped to stderr and the process exits (works even while the main thread sits inside a C call).
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("THY_WATCHDOG_SECONDS", "600")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="c3,c4")
     ap.add_argument("--out", default=None)
