@@ -157,3 +157,16 @@ def test_analytic_evidence_against_quadrature():
     lp, _ = o.linear_gaussian_batch(A, y, var, xs[:, None], prior_mean=pm, prior_var=pv, want_grad=False)
     z = np.trapezoid(np.exp(lp), xs)
     assert math.log(z) == pytest.approx(o.analytic_gaussian_log_evidence(pm, pv, A, y, var), rel=1e-9)
+
+
+def test_golden_fixture_provenance():
+    """tests/golden/extract_reference_specs.py re-reads the numbers from the reference's own test sources and recomputes
+    the derived block from the reference's formulas at 50 digits; skipped where /root/reference is absent (GPU box)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if not Path("/root/reference/src/test/scala").exists():
+        pytest.skip("reference sources not present")
+    script = Path(__file__).parent / "golden" / "extract_reference_specs.py"
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
