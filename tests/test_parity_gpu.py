@@ -301,7 +301,10 @@ def test_full_size_config2_properties():
 
 # ---- small-batch streaming kernel (B <= 8): TMA-staged memory-bound pass -----------------------------------
 STREAM_SHAPES = [(1, 1, 1), (3, 5, 2), (10, 1000, 1), (10, 1000, 8), (31, 64, 3), (32, 33, 4), (33, 257, 5), (64, 4000, 7),
-                 (100, 10_000, 1), (100, 10_000, 6), (128, 300, 8), (97, 20_000, 2)]
+                 (100, 10_000, 1), (100, 10_000, 6), (128, 300, 8), (97, 20_000, 2),
+                 # long models: every CTA goes round its TMA ring more than once; 2-8 chains then take one single-chain
+                 # pass per chain (the row-group kernel is only launched while its ring cannot wrap, kernels_stream.cu)
+                 (5, 40_000, 1), (5, 40_000, 3), (8, 50_000, 8), (20, 60_000, 16)]
 
 
 @pytest.mark.parametrize("d,n,B", STREAM_SHAPES)

@@ -440,11 +440,36 @@ bool stream_supported(const LikDev& lik, int64_t B) {
   return B >= 1 && B <= 32 && lik.dl <= 128 && fused_dmma_supported(lik, true);
 }
 
-// Auto-selection cost model (seconds): groups of 8 chains, each one pass over A at ~5.5 TB/s or a launch latency.
+// k_stream_dmma hands every stage of its ring to ONE consumer warp, a different one on each reuse of the stage.  A warp
+// reaching its wait for use u+1 of a stage while the data of use u has not landed yet would see an mbarrier parity that
+// already matches (the parity of use u-1) and run through: the parity protocol is only sound while a stage is never
+// reused inside a launch.  (Every other ring in this library has all consumer warps wait on every stage in order,
+// which cannot get a ring ahead.)  Until the kernel carries a per-stage use counter, it is therefore only launched
+// when no CTA wraps its ring; larger problems take one single-chain pass per chain (k_stream<1, T>).
+static bool stream_dmma_ring_wraps(const LikDev& lk) {
+  const int nt = fused_nt_for(lk.dl);
+  if (nt <= 0) return true;
+  const long long lds = 8 * nt + 4, np = 8 * nt;
+  const long long stage_bytes = (long long)SR * lds * 8 + SR * 16;
+  const long long red_bytes = ((long long)SNW * 8 * np + SNW * 8) * (long long)sizeof(double);
+  long long stages = (200 * 1024 - red_bytes) / stage_bytes;
+  if (stages > 16) stages = 16;
+  if (stages < 2) return true;
+  const long long nblk16 = (long long)lk.n_pad / SR;
+  long long G = sm_count();
+  if (G > nblk16) G = nblk16;
+  if (G < 1) G = 1;
+  const long long per_cta = (nblk16 + G - 1) / G;
+  return per_cta > stages;
+}
+
+// Auto-selection cost model (seconds): one pass over A at ~5.5 TB/s (or a launch latency) per group of 8 chains, or
+// per chain where the row-group kernel is not used.
 double stream_cost_model(const LikDev& lik, int64_t B) {
   const double bytes = (double)lik.n_pad * lik.lds * 8.0;
-  const double per_group = bytes / 5.5e12 > 6e-6 ? bytes / 5.5e12 : 6e-6;
-  return (double)((B + 7) / 8) * per_group;
+  const double per_pass = bytes / 5.5e12 > 6e-6 ? bytes / 5.5e12 : 6e-6;
+  const double passes = stream_dmma_ring_wraps(lik) ? (double)B : (double)((B + 7) / 8);
+  return passes * per_pass;
 }
 
 static thy_status launch_stream_group(thy_model_s* m, const LikDevOwner& lik, int B, const double* X, double* logp,
@@ -468,6 +493,17 @@ static thy_status launch_stream_group(thy_model_s* m, const LikDevOwner& lik, in
   p.log_const = lk.log_const;
   p.cauchy_sign = cauchy_sign;
   if (B <= 1) return launch_t<1>(m, p, s);   // one chain: lanes stride the columns, warp-shuffle dot products
+  if (stream_dmma_ring_wraps(lk)) {          // see stream_dmma_ring_wraps: one single-chain pass per chain
+    for (int b = 0; b < B; ++b) {
+      StreamParams q = p;
+      q.X = X + (size_t)b * m->d;
+      q.logp = logp + b;
+      q.grad = grad ? grad + (size_t)b * m->d : nullptr;
+      q.B = 1;
+      THY_TRY(launch_t<1>(m, q, s));
+    }
+    return THY_OK;
+  }
   switch (fused_nt_for(lk.dl)) {             // 2..8 chains: one DMMA row group
     case 1: return launch_dmma_nt<1>(m, p, s);
     case 2: return launch_dmma_nt<2>(m, p, s);
