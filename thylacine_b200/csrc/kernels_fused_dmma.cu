@@ -409,7 +409,7 @@ bool fused_dmma_supported(const LikDev& lik, bool want_grad) {
   return nt > 0 && lik.lds == 8 * nt + 4 && lik.n_pad % MB == 0;
 }
 
-// Auto-selection cost model (seconds): whole 64-chain tiles at ~30 TFLOP/s, plus the finish kernel.
+// Auto-selection cost model (seconds): whole 64-chain tiles at ~30 TFLOP/s, plus launch / combine overhead.
 double fused_cost_model(const LikDev& lik, int64_t B) {
   const double flops = 4.0 * lik.n_pad * (lik.lds - 4) * 64.0 * (double)((B + 63) / 64);
   const double t = flops / 30e12;
