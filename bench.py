@@ -192,6 +192,76 @@ def load_fp64_peak():
     return 37.0, "fallback: HGX B200 datasheet fp64 (37 TFLOP/s); MEASURED_PEAKS.json has no fp64 entry"
 
 
+def run_slq_leg(t, torch, dist, rank, world, stream, barrier):
+    """BASELINE configs[3] at full size.  Returns the dict that goes under the bench line's "slq" key (rank 0), timed on
+    the device (CUDA events on the model's stream), max over ranks."""
+    import math
+    from oracle import ref_oracle as o     # analytic evidence only (checker, not on the timed path)
+    d, P, A = 50, 1_000_000, 8
+    K, M = P // 16, 40
+    y = np.random.default_rng(20260104).standard_normal(d)
+    want = o.analytic_uniform_box_log_evidence(np.full(d, -10.0), np.full(d, 10.0), np.eye(d), y, np.ones(d))
+    comm = t.Communicator.fromTorchDistributed() if world > 1 else None
+
+    def build(seed):
+        post = t.UnnormalisedPosterior([t.UniformPrior.fromBounds("theta", np.full(d, 10.0), np.full(d, -10.0))],
+                                       [t.GaussianLikelihood(t.LinearForwardModel.identityOf("theta", d), y, np.full(d, 2.0))])
+        post.setStream(stream.cuda_stream)
+        cfg = t.SlqConfig(poolSize=P, abscissaNumber=A, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                          sampleParallelism=K, maxIterationCount=int(1.6 * 80 * P), minIterationCount=P)
+        return post, t.SlqIntegratedPosterior.of(cfg, post, rngSeed=seed, comm=comm, constrainedWalkSteps=M)
+
+    def max_over_ranks(v):
+        x = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return float(x.item())
+
+    # (1) the whole simulation: live phase to the engine's own termination + drain, against the analytic evidence
+    post, slq = build(6)
+    launches0 = t.kernelLaunchCount()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    slq.rebuildSampleSimulation()
+    e1.record(stream)
+    barrier()
+    sec = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+    st = slq.stats
+    launches = t.kernelLaunchCount() - launches0
+    H = st.neg_entropy_mean
+    tol = 5.0 * math.sqrt(max(H, 0.0) / P) + 3.0 * st.log_evidence_std / math.sqrt(A)
+    out = {
+        "workload": "SlqIntegratedPosterior log-evidence, 50-d Gaussian likelihood x uniform box prior, 10^6 live points "
+                    "(BASELINE configs[3]), K = P/16 retired per round, 40 constrained walk steps per replacement, 8 abscissas",
+        "scaling": "strong", "n_gpus": world, "live_points_per_gpu": P // world,
+        "seconds": sec, "rounds": int(st.rounds), "rounds_per_s": st.rounds / sec, "retired_per_s": st.iterations / sec,
+        "likelihood_evals_per_s": st.likelihood_evaluations / sec, "iterations": int(st.iterations),
+        "log_evidence": st.log_evidence_mean, "analytic_log_evidence": want, "error": st.log_evidence_mean - want,
+        "tolerance": tol, "within_tolerance": bool(abs(st.log_evidence_mean - want) < tol),
+        "neg_entropy": H, "std_over_abscissas": st.log_evidence_std, "walk_acceptance": st.walk_acceptance,
+        "gpu_launches": int(launches),
+        "collective": ("one NCCL all-gather of every rank's log-likelihoods per round on the product communicator "
+                       "(thy_comm_create, not torch.distributed)" if world > 1 else "none (single rank)"),
+    }
+    slq.close()
+    post.close()
+    # (2) where a round's time goes: a second instance, rounds as plain launches with CUDA events between the phases
+    post, slq = build(7)
+    slq.runRounds(3)
+    slq.setTrace(True)
+    slq.runRounds(12)
+    post.synchronize()
+    ph = slq.phaseTimes()
+    slq.setTrace(False)
+    out["phase_us_per_round"] = {k: (max_over_ranks(v) if k != "rounds" else v) for k, v in ph.items()}
+    slq.close()
+    post.close()
+    if comm is not None:
+        comm.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -387,6 +457,16 @@ def run_ours(args):
     except Exception as e:  # the evals/s line must not be lost to the HMC leg
         hmc_line = {"error": repr(e)}
 
+    # ---- the one path with a collective (BASELINE configs[3]): SLQ log-evidence of a 50-d Gaussian posterior with 10^6 live
+    # points SHARDED over the ranks through the product's own NCCL communicator (thy_comm_create): one all-gather of the
+    # ranks' log-likelihoods per round, radix select of the K lowest on every rank.  Strong scaling: the pool is fixed.
+    slq_line = None
+    if not args.no_slq:
+        try:
+            slq_line = run_slq_leg(t, torch, dist, rank, world, stream, barrier)
+        except Exception as e:  # the evals/s line must not be lost to the SLQ leg
+            slq_line = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = load_fp64_peak()
         k_avg_ms = k_ms.value / max(k_n.value, 1)
@@ -425,6 +505,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "reduced_flop": reduced,
             "hmc": hmc_line,
+            "slq": slq_line,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -442,6 +523,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slq", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

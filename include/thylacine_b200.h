@@ -277,7 +277,7 @@ typedef struct thy_slq_stats {
   int64_t iterations;                 /* points retired during the live phase (SlqTelemetryUpdate.iterationCount) */
   int64_t total_retired;              /* + the drained pool (SlqEngine.scala:171-180)                          */
   int64_t rounds;
-  int64_t likelihood_evaluations;
+  int64_t likelihood_evaluations;     /* walk steps of all ranks (global)                                          */
   double log_evidence_mean;           /* mean over abscissas of ln Z                                           */
   double log_evidence_std;            /* spread over abscissas                                                 */
   double neg_entropy_mean;            /* SlqTelemetryUpdate.negEntropyAvg                                      */
@@ -299,9 +299,29 @@ thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged);
 thy_status thy_slq_live_points(thy_slq_t h, int64_t* out_count, double* out_x, double* out_loglik);
 /* Retired log-likelihoods in retirement order; *out_count receives the total available. */
 thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, int64_t* out_count);
+/* ln X_i of ONE simulated abscissa (0 <= abscissa < abscissaNumber) for the retired points, in retirement order: the
+ * `abscissas` the reference keeps beside its logPdf results (SlqEngine.scala:283-297, QuadratureAbscissa.scala:33-73).
+ * Replayed on the device from the counter RNG; nothing is stored during the run. */
+thy_status thy_slq_retired_log_x(thy_slq_t h, int abscissa, int64_t max_count, double* out_log_x, int64_t* out_count);
+/* integrate(integrand) (SlqEngine.scala:460-466 -> QuadratureIntegrator.getIntegrationStats, QuadratureIntegrator.scala:64-83).
+ * The integrand is a host callback (the reference's is a JVM closure BigDecimal => BigDecimal); it receives
+ * exp(l_i - shift).  Per abscissa a: I_a = sum_i w_ai f(exp(l_i - shift)), Z_a = sum_i w_ai exp(l_i - shift);
+ * *out_reference_statistic = mean_a (I_a / Z_a - ln Z_a) -- literally what the reference returns -- and
+ * *out_integral = mean_a I_a; out_per_abscissa_integral[abscissaNumber] = I_a.  Any output may be NULL.
+ * log_shift: NaN selects the reference's (max l + min l) / 2 (BigDecimal cannot overflow; fp64 can, so pass max l for
+ * wide-ranging log-likelihoods). */
+typedef double (*thy_slq_integrand)(double scaled_likelihood, void* user);
+thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* user, double log_shift,
+                             double* out_reference_statistic, double* out_integral, double* out_per_abscissa_integral);
+/* Phase trace: while enabled, rounds run as plain launches with CUDA events between the phases (pool spread, all-gather of
+ * the ranks' keys, radix select + flags, retired values, walk + adapt, wait for the quadrature stream, round control);
+ * thy_slq_phase_times returns the mean microseconds per round of each and the number of traced rounds. */
+thy_status thy_slq_set_trace(thy_slq_t h, int enable);
+thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_rounds);
 /* Per-abscissa ln Z_a and H_a of the quadrature so far (QuadratureIntegrator.scala:29-62); [abscissaNumber] each. */
 thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, double* out_neg_entropy);
-/* sample(n) (SamplingSimulation.scala:41-101): posterior resampling of retired points; needs keepRetiredPoints. */
+/* sample(n) (SamplingSimulation.scala:41-101): every draw picks one simulated abscissa uniformly, then a retired point with
+ * probability proportional to that abscissa's trapezoid area; needs keepRetiredPoints (single GPU). */
 thy_status thy_slq_sample(thy_slq_t h, int n, uint64_t rng_seed, double* out_samples);
 
 /* ---- CartesianSurface (visualisation/CartesianSurface.scala:30-200) --------------------------------------

@@ -56,6 +56,30 @@ def main():
     for v in allv:
         assert torch.equal(v, allv[0]), "ranks disagree on the retired sequence / evidence"
     slq.close()
+
+    # --- positive log-likelihoods (tight variances; ADVICE r01: a search over uninitialised candidate memory used to bias
+    # the retire counts when logL > 0) and a pool that is not a multiple of the slice size; fixed round budget
+    d, P, K = 4, 6000, 1500
+    y = np.random.default_rng(12).standard_normal(d) * 0.01
+    post = t.UnnormalisedPosterior([t.UniformPrior.fromBounds("theta", np.full(d, 1.0), np.full(d, -1.0))],
+                                   [t.GaussianLikelihood(t.LinearForwardModel.identityOf("theta", d), y, np.full(d, 0.02))])
+    want = o.analytic_uniform_box_log_evidence(np.full(d, -1.0), np.full(d, 1.0), np.eye(d), y, np.full(d, 1e-4))
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=8, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                      sampleParallelism=K, maxIterationCount=60 * P, minIterationCount=P)
+    slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=31, comm=comm, constrainedWalkSteps=30)
+    slq.rebuildSampleSimulation()
+    ll = slq.retiredLogLikelihoods()
+    assert ll.max() > 0 and np.all(np.diff(ll) >= 0) and ll.size == slq.stats.total_retired
+    assert slq.stats.iterations % min(K, P // world // 2) == 0 or slq.stats.iterations == cfg.maxIterationCount
+    H = slq.stats.neg_entropy_mean
+    tol2 = 5.0 * math.sqrt(H / P) + 3.0 * slq.stats.log_evidence_std / math.sqrt(8)
+    assert abs(slq.logEvidence - want) < tol2, (slq.logEvidence, want, tol2)
+    mine2 = torch.tensor([slq.logEvidence, float(slq.stats.iterations), float(ll.sum())], dtype=torch.float64, device="cuda")
+    allv = [torch.empty_like(mine2) for _ in range(world)]
+    dist.all_gather(allv, mine2)
+    for v in allv:
+        assert torch.equal(v, allv[0]), "ranks disagree on the retired sequence / evidence (positive logL case)"
+    slq.close()
     comm.close()
     dist.destroy_process_group()
     if rank == 0:

@@ -302,9 +302,9 @@ def test_full_size_config2_properties():
 # ---- small-batch streaming kernel (B <= 8): TMA-staged memory-bound pass -----------------------------------
 STREAM_SHAPES = [(1, 1, 1), (3, 5, 2), (10, 1000, 1), (10, 1000, 8), (31, 64, 3), (32, 33, 4), (33, 257, 5), (64, 4000, 7),
                  (100, 10_000, 1), (100, 10_000, 6), (128, 300, 8), (97, 20_000, 2),
-                 # long models: every CTA goes round its TMA ring more than once; 2-8 chains then take one single-chain
-                 # pass per chain (the row-group kernel is only launched while its ring cannot wrap, kernels_stream.cu)
-                 (5, 40_000, 1), (5, 40_000, 3), (8, 50_000, 8), (20, 60_000, 16)]
+                 # long models: every CTA goes round its TMA ring more than once (static stage ownership keeps the
+                 # row-group kernel sound under reuse, kernels_stream.cu)
+                 (5, 40_000, 1), (5, 40_000, 3), (8, 50_000, 8), (20, 60_000, 16), (100, 300_000, 8), (128, 200_000, 5)]
 
 
 @pytest.mark.parametrize("d,n,B", STREAM_SHAPES)
@@ -319,7 +319,7 @@ def test_stream_kernel_linear_gaussian(d, n, B):
         want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
                                                   prior_var=prob["pvar"])
         lp, g = post.logPdfGradBatch(X)
-        assert post.lastKernelPath == "stream"
+        assert post.lastKernelPath == ("stream" if B == 1 else "stream_dmma")   # 2+ chains: the DMMA row-group kernel
         assert rel_err_logp(lp, want_lp) < TOL
         assert rel_err_grad(g, want_g) < TOL
         lp2, g2 = post.logPdfGradBatch(X)                       # deterministic, and the ticket was reset
@@ -332,15 +332,17 @@ def test_stream_kernel_is_the_small_batch_default_and_rejects_large_batches():
     pri = [t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])]
     lik = [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")]
     auto = t.UnnormalisedPosterior(pri, lik)
-    auto.logPdfGradBatch(typical_set_points(prob, 4, seed=1))
+    auto.logPdfGradBatch(typical_set_points(prob, 1, seed=1))
     assert auto.lastKernelPath == "stream"
+    auto.logPdfGradBatch(typical_set_points(prob, 4, seed=1))
+    assert auto.lastKernelPath == "stream_dmma"
     auto.logPdfGradBatch(typical_set_points(prob, 40, seed=1))
     assert auto.lastKernelPath == "fused_dmma"
     forced = t.UnnormalisedPosterior(pri, lik, kernelPath=capi.KERNEL_STREAM)
     X = typical_set_points(prob, 27, seed=1)                   # 4 groups of <= 8 chains, one pass over A each
     lp, g = forced.logPdfGradBatch(X)
     want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"], prior_var=prob["pvar"])
-    assert forced.lastKernelPath == "stream" and rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
+    assert forced.lastKernelPath == "stream_dmma" and rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
     with pytest.raises(t.ThylacineError) as e:
         forced.logPdfGradBatch(typical_set_points(prob, 33, seed=1))
     assert e.value.status == capi.THY_ERR_UNSUPPORTED
@@ -364,10 +366,46 @@ def test_stream_kernel_cauchy_multi_label_offset(faithful):
                       [o.cauchy_likelihood(o.LinearForwardModel(A, off), y, ci, reference_faithful=faithful)])
     X = rng.standard_normal((5, 9))
     lp, g = post.logPdfGradBatch(X)
-    assert post.lastKernelPath == "stream"
+    assert post.lastKernelPath == "stream_dmma"
     for b in range(5):
         assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
         assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+
+
+@pytest.mark.parametrize("B", [2, 4, 8])
+def test_stream_row_group_kernel_on_a_million_rows_repeated_launches_bit_identical(B):
+    """100-d / 10^6 observations / 2, 4, 8 chains runs the DMMA row-group kernel (every CTA wraps its
+    ring ~26 times), agrees with the oracle, and 1000 repeated launches are bit-identical (a stage-reuse race would show
+    up as a differing partial sum or a stall; the test is bounded by pytest-timeout)."""
+    import torch
+    d, n = 100, 1_000_000
+    rng = np.random.default_rng(4242)
+    A = rng.standard_normal((n, d)) / np.sqrt(d)
+    theta = rng.standard_normal(d)
+    y = A @ theta + 0.1 * rng.standard_normal(n)
+    ci = np.full(n, 0.2)
+    pm, pci = np.zeros(d), np.full(d, 20.0)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", pm, pci)],
+                                   [t.GaussianLinearLikelihood.of(A, y, ci, "theta")])
+    X = theta[None, :] + 0.002 * rng.standard_normal((B, d))
+    want_lp, want_g = o.linear_gaussian_batch(A, y, o.ci_to_variance(ci), X, prior_mean=pm, prior_var=o.ci_to_variance(pci))
+    lp, g = post.logPdfGradBatch(X)
+    assert post.lastKernelPath == "stream_dmma"
+    assert rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
+    Xd = torch.from_numpy(X).cuda()
+    lpd = torch.empty(B, dtype=torch.float64, device="cuda")
+    gd = torch.empty(B, d, dtype=torch.float64, device="cuda")
+    post.logPdfGradBatchDevice(B, Xd.data_ptr(), lpd.data_ptr(), gd.data_ptr())
+    torch.cuda.synchronize()
+    lp0, g0 = lpd.clone(), gd.clone()
+    assert np.array_equal(lp0.cpu().numpy(), lp) and np.array_equal(g0.cpu().numpy(), g)
+    bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    for _ in range(1000):
+        post.logPdfGradBatchDevice(B, Xd.data_ptr(), lpd.data_ptr(), gd.data_ptr())
+        bad += (lpd != lp0).sum() + (gd != g0).sum()
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+    post.close()
 
 
 # ---- wide DMMA GEMM path: d > 128 and / or non-linear links on the tensor cores -----------------------------

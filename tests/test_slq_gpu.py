@@ -83,6 +83,69 @@ def test_slq_quadrature_replays_reference_formulas():
     assert abs(slq.logEvidence - lz.mean()) < 1e-12
 
 
+def test_slq_exported_abscissas_and_integrate_follow_the_reference_quadrature():
+    """thy_slq_retired_log_x replays QuadratureAbscissa (QuadratureAbscissa.scala:33-73) for one abscissa; it must equal
+    the host replay with the device's uniforms, and thy_slq_integrate must equal QuadratureIntegrator.getIntegrationStats
+    (QuadratureIntegrator.scala:64-83) restated in numpy on those abscissas (both the literal statistic and the plain
+    quadrature)."""
+    post, _, _ = _identity_model(3, seed=8)
+    P, K, A, seed = 300, 20, 4, 5
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=A, domainScalingIncrement=0.1, targetAcceptanceProbability=0.3,
+                      sampleParallelism=K, maxIterationCount=1510, minIterationCount=100)   # last live round is partial
+    slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=seed)
+    slq.rebuildSampleSimulation()
+    ll = slq.retiredLogLikelihoods()
+    live, N = int(slq.stats.iterations), ll.size
+    assert live == 1510 and N == live + P
+    W = []
+    for a in range(A):
+        lx = slq.retiredLogX(a)
+        want = np.empty(N)
+        cur = 0.0
+        for i in range(N):
+            want[i] = cur
+            j = (i % K) if i < live else (i - live)
+            u0, _ = ph.uniform2(seed, a, 0, RNG_SLQ_SHRINK, i)
+            cur += math.log(1.0 - u0) / (P - j)
+        assert np.max(np.abs(lx - want)) < 1e-12 * max(1.0, np.max(np.abs(want)))
+        X = np.exp(lx)
+        w = np.empty(N)
+        w[0] = 0.5 * (X[0] - X[1])
+        w[1:-1] = 0.5 * (X[:-2] - X[2:])
+        w[-1] = 0.5 * (X[-2] - X[-1])
+        W.append(w)
+    f = lambda v: v * v + 0.25
+    for shift in (float(ll.max()), float("nan")):
+        s_ref = 0.5 * (ll.max() + ll.min()) if math.isnan(shift) else shift
+        e = np.exp(ll - s_ref)
+        I = np.array([np.sum(w * f(e)) for w in W])
+        Z = np.array([np.sum(w * e) for w in W])
+        assert slq.integrate(f, logShift=shift) == pytest.approx(I.mean(), rel=1e-11)
+        assert slq.integrate(f, logShift=shift, reference=True) == pytest.approx(np.mean(I / Z - np.log(Z)), rel=1e-11)
+    slq.close()
+
+
+@pytest.mark.parametrize("P,K,d", [(64, 1, 2), (1000, 500, 3), (4099, 37, 5), (2048, 1024, 2)])
+def test_slq_radix_select_retires_exactly_the_k_lowest(P, K, d):
+    """The threshold step (slq_select.cu) against numpy: after ONE round the retired values are the K smallest of the
+    initial pool, in order, every survivor is above them, and the K replacements sit above the threshold."""
+    post, _, _ = _identity_model(d, seed=P + K)
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=1, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                      sampleParallelism=K, maxIterationCount=100 * P, minIterationCount=50 * P)
+    slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=3, constrainedWalkSteps=5)
+    _, ll0 = slq.livePoints()
+    slq.runRounds(1)
+    _, ll1 = slq.livePoints()
+    ret = slq.retiredLogLikelihoods()
+    want = np.sort(ll0)[:K]
+    assert np.array_equal(ret, want)
+    thr = want[-1]
+    changed = ll1 != ll0
+    assert changed.sum() <= K and np.all(ll0[changed] <= thr)
+    assert np.all(ll1 > thr) or np.sum(ll1 <= thr) == 0
+    slq.close()
+
+
 @pytest.mark.parametrize("uniform", [True, False])
 def test_slq_log_evidence_matches_analytic(uniform):
     d, P, K = 6, 8000, 400

@@ -172,7 +172,8 @@ thy_status thy_model_collapse(thy_model_t m, thy_model_t* out) {
     rec.meas = yp;
     rec.unc = ones;
     c->liks.push_back(std::move(rec));
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = fail(THY_ERR_CUDA, "upload of the collapsed term failed");
+    // build_lik_dev uploads on stream 0, which is not ordered against an external non-blocking stream: wait for the device
+    if (cudaDeviceSynchronize() != cudaSuccess) st = fail(THY_ERR_CUDA, "upload of the collapsed term failed");
   }
   if (st != THY_OK) {
     thy_model_destroy(c);

@@ -92,7 +92,10 @@ thy_status thy_comm_create(int rank, int world, const unsigned char unique_id[12
   c->rank = rank;
   c->world = world;
   if (world > 1) {
-    THY_TRY(require_device());
+    if (require_device() != THY_OK) {
+      delete c;
+      return THY_ERR_NO_DEVICE;
+    }
     if (!unique_id) {
       delete c;
       return fail(THY_ERR_INVALID_ARGUMENT, "unique id required for world > 1");

@@ -35,9 +35,10 @@ thy_status launch_wide_likelihood(thy_model_s* m, LikDevOwner& lik, int64_t B, c
 
 // slq_walk.cu -- SLQ replacement step (spawn + M constrained walk steps + commit) as one kernel for small linear models
 bool slq_walk_supported(const thy_model_s* m);
-thy_status launch_slq_walk(thy_model_s* m, int c, long long Pl, int M, uint64_t seed, uint64_t round, int rank,
-                           const int* sidx, double* x, double* ll, double* lpr, const double* sigma, const double* scalars,
-                           int* accepted, cudaStream_t s);
+// c_max sizes the grid; the walker count and the round number are read from device words (graph replay)
+thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long long Pl, int M, uint64_t seed,
+                           const long long* round_dev, int rank, const int* sidx, const unsigned char* flags, double* x,
+                           double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s);
 
 // link functions (device), shared by the generic and FD kernels
 __device__ __forceinline__ double link_eval(int link, double z) {

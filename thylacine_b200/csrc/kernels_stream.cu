@@ -256,18 +256,39 @@ __global__ void __launch_bounds__((SNW + 1) * 32, 1) k_stream(const StreamParams
 // Eight chains are exactly one DMMA.8x8x4 row group, so the per-row work drops from ~90 DFMA + a shuffle tree to
 // 6.5 DMMA and the pass stays HBM-bound (3.7 flop/B at 8 chains vs a ridge of 5.5).  Same fragment scheme as the fused
 // kernel (GEMM1's C fragment is GEMM2's A fragment through the row permutation pi; pitch = 4 mod 8 => conflict-free),
-// but the warps of a CTA split ROW blocks instead of chain groups: warp w owns 16-row stages w, w + 8, ... of the ring.
-constexpr int SR = 16;       // rows per stage
-constexpr int SJG = SR / 8;  // 8-row groups per stage
+// but the warps of a CTA split ROW blocks instead of chain groups: item i (8 rows) of a CTA belongs to warp i % SNW.
+//
+// Ring protocol (round 2: STATIC STAGE OWNERSHIP).  The ring depth is a multiple of SNW, so stage s = i % stages is
+// always consumed by warp s % SNW -- the same warp on every reuse of the stage.  A warp takes its items in increasing
+// order, hence it reaches the wait for use u+1 of a stage only after its own wait for use u has returned, i.e. after
+// phase u of the stage's full barrier has completed; and the producer re-arms the stage for use u+1 only after that
+// warp's arrival on the empty barrier for use u.  The full barrier is therefore never more than one phase away from the
+// phase the waiting warp names, which is exactly the condition under which mbarrier.try_wait.parity is unambiguous.
+// (Round 1 handed a stage to a DIFFERENT warp on each reuse; a warp one use ahead could then pass its wait on the
+// parity of use u-1 and read stale data.  That guard, stream_dmma_ring_wraps, is gone: every model length runs here.)
+constexpr int SR = 8;        // rows per stage = one DMMA row group
+
+template <int NT>
+struct StreamDmmaCfg {
+  static constexpr int NP = 8 * NT, KS = 2 * NT, LDS = 8 * NT + 4;
+  static constexpr int A_BYTES = SR * LDS * 8, STAGE_BYTES = A_BYTES + SR * 16;
+  static constexpr size_t RED_BYTES = (size_t)(SNW * 8 * NP + SNW * 8) * sizeof(double);
+  // ring depth: as many stages as fit beside the reduction scratch, rounded DOWN to a multiple of SNW (static ownership)
+  static constexpr int STAGES_FIT = (int)((200 * 1024 - RED_BYTES) / STAGE_BYTES);
+  static constexpr int STAGES = (STAGES_FIT / SNW) * SNW > 4 * SNW ? 4 * SNW : (STAGES_FIT / SNW) * SNW;
+  static_assert(STAGES >= SNW && STAGES % SNW == 0, "the row-group ring needs at least one stage per consumer warp");
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + RED_BYTES;
+};
 
 template <int NT>
 __global__ void __launch_bounds__((SNW + 1) * 32, 1) k_stream_dmma(const StreamParams p) {
-  constexpr int NP = 8 * NT, KS = 2 * NT, LDS = 8 * NT + 4;
-  constexpr int A_BYTES = SR * LDS * 8, STAGE_BYTES = A_BYTES + SR * 16;
+  using C = StreamDmmaCfg<NT>;
+  constexpr int NP = C::NP, KS = C::KS, LDS = C::LDS, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + p.stages;
-  double* red = reinterpret_cast<double*>(empty_bar + p.stages);   // [SNW][8][NP]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  double* red = reinterpret_cast<double*>(empty_bar + STAGES);   // [SNW][8][NP]
   double* redq = red + SNW * 8 * NP;
   __shared__ int s_last;
   __shared__ double s_q[8];
@@ -278,9 +299,9 @@ __global__ void __launch_bounds__((SNW + 1) * 32, 1) k_stream_dmma(const StreamP
   const int nb = blk1 - blk0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);   // a stage is consumed by exactly one warp
+      ptx::mbar_init(&empty_bar[s], 1);   // a stage is consumed by exactly one warp, always the same one
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -289,14 +310,18 @@ __global__ void __launch_bounds__((SNW + 1) * 32, 1) k_stream_dmma(const StreamP
 
   if (warp == SNW) {
     if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
       for (int i = 0; i < nb; ++i) {
-        const int stage = i % p.stages;
-        const uint32_t phase = (uint32_t)((i / p.stages) & 1);
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         unsigned char* dst = smem + (size_t)stage * STAGE_BYTES;
         ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
         ptx::bulk_g2s(dst, p.A + (size_t)(blk0 + i) * SR * LDS, A_BYTES, &full_bar[stage]);
         ptx::bulk_g2s(dst + A_BYTES, p.yiv + (size_t)(blk0 + i) * SR, SR * 16, &full_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
@@ -317,42 +342,41 @@ __global__ void __launch_bounds__((SNW + 1) * 32, 1) k_stream_dmma(const StreamP
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) ga[t][0] = ga[t][1] = 0.0;
+    // this warp's stages are warp, warp + SNW, ... (STAGES / SNW of them), visited round-robin
+    int stage = warp;
+    uint32_t phase = 0;
     for (int i = warp; i < nb; i += SNW) {
-      const int stage = i % p.stages;
-      const uint32_t phase = (uint32_t)((i / p.stages) & 1);
       ptx::mbar_wait(&full_bar[stage], phase);
       const double* As = reinterpret_cast<const double*>(smem + (size_t)stage * STAGE_BYTES);
       const double2* Ys = reinterpret_cast<const double2*>(smem + (size_t)stage * STAGE_BYTES + A_BYTES);
-      double z[SJG][2];
+      // GEMM1 as two interleaved accumulator chains (even / odd k4 steps), summed afterwards
+      double z0 = 0.0, z1 = 0.0, u0 = 0.0, u1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < SJG; ++j) z[j][0] = z[j][1] = 0.0;
-#pragma unroll
-      for (int kk = 0; kk < KS; ++kk) {
-#pragma unroll
-        for (int j = 0; j < SJG; ++j) ptx::dmma884(z[j][0], z[j][1], xf[kk], As[off1 + j * 8 * LDS + 4 * kk]);
+      for (int kk = 0; kk + 1 < KS; kk += 2) {
+        ptx::dmma884(z0, z1, xf[kk], As[off1 + 4 * kk]);
+        ptx::dmma884(u0, u1, xf[kk + 1], As[off1 + 4 * (kk + 1)]);
       }
-#pragma unroll
-      for (int j = 0; j < SJG; ++j) {
-        const double2 y0 = Ys[j * 8 + pi_s0];
-        const double2 y1 = Ys[j * 8 + pi_s1];
-        const double r0 = y0.x - z[j][0], r1 = y1.x - z[j][1];
-        const double w0 = r0 * y0.y, w1 = r1 * y1.y;
-        ssq = fma(r0, w0, ssq);
-        ssq = fma(r1, w1, ssq);
-        z[j][0] = w0;
-        z[j][1] = w1;
-      }
+      z0 += u0;
+      z1 += u1;
+      const double2 y0 = Ys[pi_s0];
+      const double2 y1 = Ys[pi_s1];
+      const double r0 = y0.x - z0, r1 = y1.x - z1;
+      const double w0 = r0 * y0.y, w1 = r1 * y1.y;
+      ssq = fma(r0, w0, ssq);
+      ssq = fma(r1, w1, ssq);
       if (p.grad) {
 #pragma unroll
-        for (int j = 0; j < SJG; ++j) {
+        for (int t = 0; t < NT; ++t) ptx::dmma884(ga[t][0], ga[t][1], w0, As[off2_s0 + 8 * t]);
 #pragma unroll
-          for (int t = 0; t < NT; ++t) ptx::dmma884(ga[t][0], ga[t][1], z[j][0], As[off2_s0 + j * 8 * LDS + 8 * t]);
-#pragma unroll
-          for (int t = 0; t < NT; ++t) ptx::dmma884(ga[t][0], ga[t][1], z[j][1], As[off2_s1 + j * 8 * LDS + 8 * t]);
-        }
+        for (int t = 0; t < NT; ++t) ptx::dmma884(ga[t][0], ga[t][1], w1, As[off2_s1 + 8 * t]);
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+      stage += SNW;
+      if (stage >= STAGES) {
+        stage = warp;
+        phase ^= 1;
+      }
     }
     const double qsum = quad_sum(ssq);
     if (q4 == 0) redq[warp * 8 + g8] = qsum;
@@ -365,18 +389,12 @@ __global__ void __launch_bounds__((SNW + 1) * 32, 1) k_stream_dmma(const StreamP
 
 template <int NT>
 thy_status launch_dmma_nt(thy_model_s* m, StreamParams& p, cudaStream_t s) {
-  constexpr int NP = 8 * NT, LDS = 8 * NT + 4;
-  constexpr int STAGE_BYTES = SR * LDS * 8 + SR * 16;
-  const size_t red_bytes = (size_t)(SNW * 8 * NP + SNW * 8) * sizeof(double);
-  int stages = (int)((200 * 1024 - red_bytes) / STAGE_BYTES);
-  if (stages > 16) stages = 16;
-  if (stages < 2) return fail(THY_ERR_UNSUPPORTED, "streaming kernel: tile does not fit shared memory");
-  p.stages = stages;
-  p.nblk = p.nblk * (SMB / SR);   // 16-row blocks
-  const size_t smem = (size_t)stages * STAGE_BYTES + 2 * stages * sizeof(uint64_t) + red_bytes;
+  using C = StreamDmmaCfg<NT>;
+  p.stages = C::STAGES;
+  p.nblk = p.nblk * (SMB / SR);   // 8-row blocks
   int G = sm_count();
   if (G > p.nblk) G = p.nblk;
-  THY_TRY(m->ws.partG.reserve((size_t)G * 8 * NP));
+  THY_TRY(m->ws.partG.reserve((size_t)G * 8 * C::NP));
   THY_TRY(m->ws.partL.reserve((size_t)G * 8));
   if (!m->ws.ticket.ptr) {
     THY_TRY(m->ws.ticket.reserve(1));
@@ -385,9 +403,9 @@ thy_status launch_dmma_nt(thy_model_s* m, StreamParams& p, cudaStream_t s) {
   p.partG = m->ws.partG.ptr;
   p.partL = m->ws.partL.ptr;
   p.ticket = m->ws.ticket.ptr;
-  THY_CUDA_CHECK(cudaFuncSetAttribute(k_stream_dmma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  THY_CUDA_CHECK(cudaFuncSetAttribute(k_stream_dmma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   KernelTimer timer(m, s);
-  k_stream_dmma<NT><<<G, (SNW + 1) * 32, smem, s>>>(p);
+  k_stream_dmma<NT><<<G, (SNW + 1) * 32, C::SMEM, s>>>(p);
   timer.stop();
   count_launch();
   THY_CUDA_CHECK(cudaGetLastError());
@@ -440,36 +458,11 @@ bool stream_supported(const LikDev& lik, int64_t B) {
   return B >= 1 && B <= 32 && lik.dl <= 128 && fused_dmma_supported(lik, true);
 }
 
-// k_stream_dmma hands every stage of its ring to ONE consumer warp, a different one on each reuse of the stage.  A warp
-// reaching its wait for use u+1 of a stage while the data of use u has not landed yet would see an mbarrier parity that
-// already matches (the parity of use u-1) and run through: the parity protocol is only sound while a stage is never
-// reused inside a launch.  (Every other ring in this library has all consumer warps wait on every stage in order,
-// which cannot get a ring ahead.)  Until the kernel carries a per-stage use counter, it is therefore only launched
-// when no CTA wraps its ring; larger problems take one single-chain pass per chain (k_stream<1, T>).
-static bool stream_dmma_ring_wraps(const LikDev& lk) {
-  const int nt = fused_nt_for(lk.dl);
-  if (nt <= 0) return true;
-  const long long lds = 8 * nt + 4, np = 8 * nt;
-  const long long stage_bytes = (long long)SR * lds * 8 + SR * 16;
-  const long long red_bytes = ((long long)SNW * 8 * np + SNW * 8) * (long long)sizeof(double);
-  long long stages = (200 * 1024 - red_bytes) / stage_bytes;
-  if (stages > 16) stages = 16;
-  if (stages < 2) return true;
-  const long long nblk16 = (long long)lk.n_pad / SR;
-  long long G = sm_count();
-  if (G > nblk16) G = nblk16;
-  if (G < 1) G = 1;
-  const long long per_cta = (nblk16 + G - 1) / G;
-  return per_cta > stages;
-}
-
-// Auto-selection cost model (seconds): one pass over A at ~5.5 TB/s (or a launch latency) per group of 8 chains, or
-// per chain where the row-group kernel is not used.
+// Auto-selection cost model (seconds): one pass over A at ~5.5 TB/s (or a launch latency) per group of 8 chains.
 double stream_cost_model(const LikDev& lik, int64_t B) {
   const double bytes = (double)lik.n_pad * lik.lds * 8.0;
   const double per_pass = bytes / 5.5e12 > 6e-6 ? bytes / 5.5e12 : 6e-6;
-  const double passes = stream_dmma_ring_wraps(lik) ? (double)B : (double)((B + 7) / 8);
-  return passes * per_pass;
+  return (double)((B + 7) / 8) * per_pass;
 }
 
 static thy_status launch_stream_group(thy_model_s* m, const LikDevOwner& lik, int B, const double* X, double* logp,
@@ -493,17 +486,7 @@ static thy_status launch_stream_group(thy_model_s* m, const LikDevOwner& lik, in
   p.log_const = lk.log_const;
   p.cauchy_sign = cauchy_sign;
   if (B <= 1) return launch_t<1>(m, p, s);   // one chain: lanes stride the columns, warp-shuffle dot products
-  if (stream_dmma_ring_wraps(lk)) {          // see stream_dmma_ring_wraps: one single-chain pass per chain
-    for (int b = 0; b < B; ++b) {
-      StreamParams q = p;
-      q.X = X + (size_t)b * m->d;
-      q.logp = logp + b;
-      q.grad = grad ? grad + (size_t)b * m->d : nullptr;
-      q.B = 1;
-      THY_TRY(launch_t<1>(m, q, s));
-    }
-    return THY_OK;
-  }
+  m->last_path = "stream_dmma";              // 2..8 chains: one DMMA row group, any model length
   switch (fused_nt_for(lk.dl)) {             // 2..8 chains: one DMMA row group
     case 1: return launch_dmma_nt<1>(m, p, s);
     case 2: return launch_dmma_nt<2>(m, p, s);

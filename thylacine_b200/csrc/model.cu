@@ -82,6 +82,7 @@ void spd_inverse(const std::vector<double>& L, int n, std::vector<double>& P) {
 
 static thy_status check_model(thy_model_t m, bool want_finalized) {
   if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
+  if (m->poisoned) return fail(THY_ERR_STATE, "an earlier thy_model_finalize failed on this handle; destroy it and build a new model");
   if (want_finalized && !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (!want_finalized && m->finalized) return fail(THY_ERR_STATE, "model is already finalized (immutable)");
   return THY_OK;
@@ -361,8 +362,21 @@ thy_status thy_model_set_option(thy_model_t m, int option, int value) {
   }
 }
 
+// A finalize that fails half-way (non-SPD covariance, unknown label, failed upload) leaves host vectors and device
+// buffers partially filled and the coefficient blocks of earlier likelihoods already released: the handle is marked
+// poisoned and every later call on it reports THY_ERR_STATE (the caller destroys it and builds a new model).
+static thy_status finalize_impl(thy_model_t m);
 thy_status thy_model_finalize(thy_model_t m) {
   THY_TRY(check_model(m, false));
+  const thy_status st = finalize_impl(m);
+  if (st != THY_OK && st != THY_ERR_NO_DEVICE) m->poisoned = true;
+  return st;
+}
+static thy_status finalize_impl(thy_model_t m) {
+  m->h_chol_off.clear();
+  m->pr_precisions.clear();
+  m->lik_dev.clear();
+  m->layout.clear();
   if (m->priors.empty()) return fail(THY_ERR_INVALID_ARGUMENT, "a posterior needs at least one prior");
   THY_TRY(require_device());
   THY_CUDA_CHECK(cudaGetDevice(&m->device));

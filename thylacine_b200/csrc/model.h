@@ -97,6 +97,7 @@ struct thy_model_s {
   std::vector<thy::PriorHost> priors;
   std::vector<thy::LikelihoodHost> liks;
   bool finalized = false;
+  bool poisoned = false;   // a finalize failed half-way: the handle only accepts thy_model_destroy
   int d = 0;
   int opt_cauchy_ref_sign = 1;
   int opt_fd_incremental = 0;

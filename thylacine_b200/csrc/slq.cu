@@ -6,19 +6,24 @@
 //   SlqEngine.scala:171-180        drainSamplePool: remaining live points appended in ascending order
 //   QuadratureAbscissa.scala:33-73 prior-mass simulation: pool of P uniforms, max moved to the abscissa list (first = 1.0),
 //                                  trapezoid weights 1/2 (X_{i-1} - X_{i+1}), ends half the adjacent gap
-//   QuadratureIntegrator.scala:29-62  Z_a = sum w_i exp(l_i - s), H_a = sum w_i e^{l_i - s}(l_i - s)/Z_a - ln Z_a
+//   QuadratureIntegrator.scala:29-83  Z_a, H_a and getIntegrationStats per abscissa
+//   SamplingSimulation.scala:41-101   posterior resampling of the retired points, one simulated abscissa per draw
 // Re-design for 10^6 live points (DESIGN.md "SLQ"): the K lowest live points are retired per round (K = sampleParallelism,
-// the reference's number of concurrent sampling fibres); thresholds come from a device radix sort plus, across GPUs, an
-// NCCL all-gather of each rank's K smallest; replacements are constrained random walks started from surviving live
-// points (the reference's O(P^2 d) cubical cover cannot exist at this size); prior-mass shrinkage is sampled directly as
-// t = u^{1/n_live} per abscissa in log space and the evidence is a streaming log-sum-exp (no BigDecimal needed).
+// the reference's number of concurrent sampling fibres).  A round is
+//     spread of the pool -> [all-gather of the ranks' log-likelihoods] -> radix SELECT of the K-th smallest (slq_select.cu,
+//     no sort) -> retire flags / slots -> fused constrained walk (slq_walk.cu) -> scale adaptation,
+// with the quadrature update (sort of the K retired values, prior-mass simulation, log-sum-exp; slq_evidence.cu) on a
+// side stream beside the walk.  Nothing in a round needs the host: the retirement counter, the round number and the
+// convergence verdict live in device memory, so a full round is ONE CUDA-graph launch and the host runs two rounds
+// ahead of the device; it learns about convergence from a write-once device word with a fixed lag, which makes the
+// stopping round identical on every rank (they all compute the same evidence from the same gathered keys).
 // Measure / integrand: points are drawn from the PRIOR and ranked by log-LIKELIHOOD, so ln Z is the calibrated
 // evidence (for uniform priors this coincides with the reference's uniform-domain / full-density formulation, Q6).
-#include "kernels.h"
+#include "slq_internal.h"
 #include "comm.h"
-#include "philox.cuh"
 #include <cub/cub.cuh>
 #include <cmath>
+#include <climits>
 #include <algorithm>
 #include <chrono>
 
@@ -31,152 +36,104 @@ struct thy_slq_s {
   long long P = 0, Pl = 0;   // global / local live points
   int d = 0, A = 1, K = 1, M = 20;
   thy::DevBuf<double> x, ll, lpr;                        // live pool
-  thy::DevBuf<double> keys_in, keys_out;                 // sort scratch
-  thy::DevBuf<int> idx_in, idx_out;
+  thy::DevBuf<double> keys_all;                          // [P] log-likelihoods of all ranks (world > 1)
+  // threshold selection (slq_select.cu)
+  thy::DevBuf<thy::SelectState> sel_state;
+  thy::DevBuf<unsigned int> sel_hist, sel_ticket, sel_cursor;
+  thy::DevBuf<int2> sel_cnt;
+  thy::DevBuf<unsigned char> flags;
+  thy::DevBuf<int> sidx, count_dev;
+  thy::DevBuf<double> vals_raw, vals_sorted;             // retired values of the round, unordered / ascending
+  thy::DevBuf<int> pair_in, pair_out;                    // slot ids beside the keys (drain / keepRetiredPoints)
   thy::DevBuf<unsigned char> cub_tmp;
-  thy::DevBuf<double> cand_all, cand_sorted;             // gathered candidates
-  thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers
+  thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers of the per-step path
   thy::DevBuf<int> slot, accepted;
   thy::DevBuf<double> sigma, sig_part;                   // per-dimension spread of the live pool
-  thy::DevBuf<double> scalars;                           // [0] walk scale, [1] threshold, [2] accepted, [3] proposed
-  thy::DevBuf<int> count_dev;                            // [0] local retire count
-  thy::DevBuf<double> tmp_logx;                          // [A][Kmax]
-  thy::DevBuf<double> abs_state;                         // [A][8]: logX_cur, Xm2, Xm1, pend_l, has_pend(0/1/2), m, s, s_l
-  thy::DevBuf<double> abs_out;                           // [A][2]: logZ, H
+  thy::DevBuf<double> scalars;                           // [0] walk scale, [1] threshold, [4] last rate, [5] accepted, [6] proposed
+  // quadrature (slq_evidence.cu)
+  thy::DevBuf<double> ev_lt, ev_segsum, ev_part, abs_state, abs_out;
+  thy::DevBuf<unsigned int> ev_tickets;
   thy::DevBuf<double> ret_ll;                            // retired log-likelihoods (global order)
   thy::DevBuf<double> ret_x;                             // retired points (optional, world == 1)
-  thy::DevBuf<double> ret_logw;                          // log posterior weight under the expected abscissa
-  long long iterations = 0, rounds = 0, evals = 0;
+  thy::DevBuf<long long> ctl;                            // [0] iterations, [1] round, [2] first converged round (-1: none)
+  long long iterations = 0, rounds = 0, evals = 0;       // host mirrors of ctl[0], ctl[1]
+  long long live_iterations = -1;                        // set by the drain
   long long ret_capacity = 0;
   bool fused_walk = false;             // slq_walk.cu covers this model: one kernel per round instead of 5 per walk step
-  cudaStream_t side = nullptr;         // evidence accumulation runs beside the walk (it only needs the retired values)
-  cudaEvent_t ev_retired = nullptr, ev_evidence = nullptr;
-  double* host_ao = nullptr;           // pinned [A][2] copy of abs_out for the convergence test
-  int* host_c = nullptr;               // pinned copy of the local retire count
-  long long* host_it = nullptr;        // pinned staging of `iterations` for the device-side round control
-  thy::DevBuf<long long> ctl;          // [0] iterations at the start of the round (read by graph-captured kernels)
-  cudaStream_t select_graph_stream = nullptr;
-  cudaGraphExec_t select_graph = nullptr;   // the selection phase of a full round (sigma, sort, gather, merge, threshold)
+  cudaStream_t side = nullptr;         // quadrature update runs beside the walk
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_round[3] = {};        // completion of round r is ev_round[r % 3]
+  double* host_ao = nullptr;           // pinned [A][2] copy of abs_out
+  int* host_c = nullptr;               // pinned copy of the local retire count (per-step path)
+  long long* host_conv = nullptr;      // pinned copy of ctl[2]
+  cudaStream_t graph_stream = nullptr;
+  cudaGraphExec_t graph = nullptr;     // one full round (Kr == K)
+  uint64_t graph_launches = 0;
   bool use_graph = true;
-  // THY_SLQ_TRACE=1: CUDA-event phase times of the round (sort / gather / merge+threshold / replace), printed at destroy
+  bool sort_sized = false;             // cub scratch sized (first round runs outside the graph)
+  // phase trace (thy_slq_set_trace / THY_SLQ_TRACE=1): CUDA-event times of the round's phases, plain launches
   bool trace = false;
-  cudaEvent_t tev[6] = {};
-  double tsum[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t tev[8] = {};
+  double tsum[7] = {0, 0, 0, 0, 0, 0, 0};
   long long tcount = 0;
-  // THY_SLQ_TRACE=2: host wall-clock split of the round (graph replay stays on): enqueue / wait for the retire count /
-  // enqueue of the replacement step / wait for the evidence update
-  bool htrace = false;
-  double hsum[4] = {0, 0, 0, 0};
-  long long hcount = 0;
   bool finished = false;
+  thy_slq_stats stats{};
   ~thy_slq_s() {
+    if (graph) cudaGraphExecDestroy(graph);
     if (side) cudaStreamDestroy(side);
-    if (ev_retired) cudaEventDestroy(ev_retired);
-    if (ev_evidence) cudaEventDestroy(ev_evidence);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    for (auto& e : ev_round) if (e) cudaEventDestroy(e);
+    for (auto& e : tev) if (e) cudaEventDestroy(e);
     if (host_ao) cudaFreeHost(host_ao);
     if (host_c) cudaFreeHost(host_c);
-    if (host_it) cudaFreeHost(host_it);
-    if (select_graph) cudaGraphExecDestroy(select_graph);
-    if (htrace && hcount > 0)
-      std::fprintf(stderr, "[thy slq host trace] rank %d: %lld rounds, graph %s; host us/round: enqueue selection %.1f, wait count %.1f, "
-                   "enqueue replacement %.1f, wait evidence %.1f\n", rank, hcount, select_graph ? "on" : "off",
-                   1e6 * hsum[0] / hcount, 1e6 * hsum[1] / hcount, 1e6 * hsum[2] / hcount, 1e6 * hsum[3] / hcount);
-    if (trace) {
-      if (tcount > 0)
-        std::fprintf(stderr, "[thy slq trace] rank %d: %lld rounds; us/round: sigma %.1f, local sort %.1f, all-gather %.1f, "
-                     "merge+threshold %.1f, replace+adapt %.1f\n", rank, tcount, 1e3 * tsum[0] / tcount, 1e3 * tsum[1] / tcount,
-                     1e3 * tsum[2] / tcount, 1e3 * tsum[3] / tcount, 1e3 * tsum[4] / tcount);
-      for (auto& e : tev) if (e) cudaEventDestroy(e);
-    }
+    if (host_conv) cudaFreeHost(host_conv);
   }
-  thy_slq_stats stats{};
 };
 
 namespace thy {
+
+static const char* const kPhaseNames[7] = {"pool spread", "all-gather of keys", "radix select + flags", "retired values",
+                                           "walk + adapt", "wait for quadrature", "round control"};
 
 __global__ void k_iota(int n, int* v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = i;
 }
 
-__global__ void k_fill(long long n, double* v, double val) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = val;
-}
-
-// threshold = merged[Kr-1].  Exactly Kr points are retired globally even when log-likelihoods tie (a walker that never
-// moved is an exact copy of a survivor; the reference nudges duplicates by one ulp instead, SlqEngine.scala:107-118):
-// every value < threshold goes, and the ties at the threshold are taken in rank order, lowest sorted index first.
-__device__ __forceinline__ long long lower_bound_dev(const double* v, long long n, double x) {  // first index with v >= x
-  long long lo = 0, hi = n;
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (v[mid] < x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-__device__ __forceinline__ long long upper_bound_dev(const double* v, long long n, double x) {  // first index with v > x
-  long long lo = 0, hi = n;
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (v[mid] <= x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-// Merge of the ranks' sorted candidate lists: element (r, i) computes its position in the union -- values from lower
-// ranks win ties, then the position inside the list -- and the Kr smallest land in `merged` in ascending order.
-// One launch instead of a radix sort of Kr * world keys.
-__global__ void __launch_bounds__(256) k_slq_merge(const double* __restrict__ cand_all, int Kr, int world,
-                                                   double* __restrict__ merged) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)Kr * world) return;
-  const int r = (int)(e / Kr), i = (int)(e % Kr);
-  const double v = cand_all[e];
-  long long pos = i;
-  for (int q = 0; q < world; ++q) {
-    if (q == r) continue;
-    const double* lst = cand_all + (size_t)q * Kr;
-    // the smallest value of a list that is already beyond v contributes nothing; skip its search
-    if (lst[0] > v) continue;
-    pos += (q < r) ? upper_bound_dev(lst, Kr, v) : lower_bound_dev(lst, Kr, v);
-    if (pos >= Kr) return;
-  }
-  if (pos < Kr) merged[pos] = v;
-}
-
 // retired values recorded in global order at ret_ll[iterations ...] (iterations read from the device-side control
 // word so that the launch can live inside a CUDA graph)
-__global__ void __launch_bounds__(256) k_slq_copy_retired(const double* __restrict__ merged, int Kr,
+__global__ void __launch_bounds__(256) k_slq_copy_retired(const double* __restrict__ sorted, int Kr,
                                                           const long long* __restrict__ ctl, double* __restrict__ ret_ll) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Kr) ret_ll[ctl[0] + i] = merged[i];
+  if (i < Kr) ret_ll[ctl[0] + i] = sorted[i];
 }
 
-__global__ void k_slq_threshold(const double* __restrict__ merged, int Kr, const double* __restrict__ local_sorted,
-                                const double* __restrict__ cand_all, int world, int rank,
-                                double* __restrict__ scalars, int* __restrict__ count) {
+// Convergence test of the reference (SlqEngine.scala:249-262: iterations > minIterationCount && iterations >= 10 P H) on
+// the device: the first round at which it holds is written ONCE to ctl[2].
+__global__ void k_slq_converge(long long* __restrict__ ctl, const double* __restrict__ abs_out, int A, int Kr, double P,
+                               long long min_iterations) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double thr = merged[Kr - 1];
-  scalars[1] = thr;
-  if (world == 1) {
-    count[0] = Kr;
-    return;
-  }
-  const long long below = lower_bound_dev(merged, (long long)Kr * world, thr);
-  long long need = Kr - below;  // ties still to take, >= 1
-  long long mine = 0;
-  for (int r = 0; r <= rank; ++r) {
-    const double* cr = cand_all + (size_t)r * Kr;
-    const long long ties = upper_bound_dev(cr, Kr, thr) - lower_bound_dev(cr, Kr, thr);
-    const long long take = ties < need ? ties : need;
-    if (r == rank) mine = take;
-    need -= take;
-  }
-  count[0] = (int)(lower_bound_dev(local_sorted, Kr, thr) + mine);
+  double hmax = -INFINITY;
+  for (int a = 0; a < A; ++a) hmax = fmax(hmax, abs_out[a * 2 + 1]);
+  const long long it = ctl[0] + Kr;
+  if (ctl[2] < 0 && it > min_iterations && isfinite(hmax) && (double)it >= 10.0 * P * hmax) ctl[2] = ctl[1];
+}
+__global__ void k_slq_advance(long long* __restrict__ ctl, int Kr) {
+  ctl[0] += Kr;
+  ctl[1] += 1;
+}
+// key of every retired slot (for the index sort of keepRetiredPoints)
+__global__ void __launch_bounds__(256) k_slq_slot_keys(int c, const int* __restrict__ sidx, const double* __restrict__ ll,
+                                                       double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) out[i] = ll[sidx[i]];
 }
 
 // Per-dimension standard deviation of the live pool: deterministic two-stage reduction.
-__global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, int d, const double* __restrict__ x,
+// Pl = number of SAMPLED rows; sampled row r is pool row r * row_stride (a strided subsample of at most 65 536 points
+// estimates the spread to well under a percent; it only sets the proposal scale, which any positive value keeps valid).
+__global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, long long row_stride, int d, const double* __restrict__ x,
                                                         double* __restrict__ part, int nslab) {
   // block = one slab of rows, read as one contiguous stream (fully coalesced); thread t always sees the same column
   // phase because the stride 256 * k is re-based per row group: element e of the slab has column (e0 + e) % d
@@ -191,7 +148,7 @@ __global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, int d, con
     const int rr = threadIdx.x / d, j = threadIdx.x % d;
     if (rr < rows_per_pass) {
       for (long long r = r0 + rr; r < r1; r += rows_per_pass) {
-        const double v = x[r * d + j];
+        const double v = x[r * row_stride * d + j];
         s += v;
         s2 = fma(v, v, s2);
       }
@@ -213,7 +170,7 @@ __global__ void __launch_bounds__(256) k_slq_sigma_part(long long Pl, int d, con
       s = 0.0;
       s2 = 0.0;
       for (long long r = r0; r < r1; ++r) {
-        const double v = x[r * d + j];
+        const double v = x[r * row_stride * d + j];
         s += v;
         s2 = fma(v, v, s2);
       }
@@ -241,19 +198,16 @@ __global__ void __launch_bounds__(256) k_slq_sigma_final(long long Pl, int d, co
   sigma[j] = sqrt(var);
 }
 
-// Walkers start from uniformly chosen survivors.
+// Walkers start from uniformly chosen survivors (slq_pick_survivor: the same draw as the fused walk kernel).
 __global__ void __launch_bounds__(256) k_slq_spawn(int c, long long Pl, int d, uint64_t seed, uint64_t round, int rank,
-                                                   const int* __restrict__ sidx, const double* __restrict__ x,
-                                                   const double* __restrict__ ll, const double* __restrict__ lpr,
-                                                   double* __restrict__ Y, double* __restrict__ yl, double* __restrict__ ypr,
-                                                   int* __restrict__ slot) {
+                                                   const int* __restrict__ sidx, const unsigned char* __restrict__ flags,
+                                                   const double* __restrict__ x, const double* __restrict__ ll,
+                                                   const double* __restrict__ lpr, double* __restrict__ Y,
+                                                   double* __restrict__ yl, double* __restrict__ ypr, int* __restrict__ slot) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= c) return;
-  const RngDraw u = rng_uniform2(seed, ((uint64_t)rank << 40) | (uint64_t)w, 0, RNG_SLQ_PICK, round);
-  long long pick = c + (long long)(u.u0 * (double)(Pl - c));
-  if (pick >= Pl) pick = Pl - 1;
-  const int src = sidx[pick];
+  const long long src = slq_pick_survivor(seed, ((uint64_t)rank << 40) | (uint64_t)w, round, Pl, flags);
   for (int j = lane; j < d; j += 32) Y[(size_t)w * d + j] = x[(size_t)src * d + j];
   if (lane == 0) {
     yl[w] = ll[src];
@@ -315,9 +269,10 @@ __global__ void __launch_bounds__(256) k_slq_commit(int c, int d, const int* __r
 
 // scale *= (1 + inc) when the round's acceptance beat the target, else /= (1 + inc)   (SlqConfig.domainScalingIncrement,
 // targetAcceptanceProbability play the same role for the reference's cube scaling, QuadratureDomainTelemetry.scala)
-__global__ void __launch_bounds__(1024) k_slq_adapt(double* scalars, double inc, double target, int c, int steps,
-                                                    int* __restrict__ accepted) {
+__global__ void __launch_bounds__(1024) k_slq_adapt(double* scalars, double inc, double target, const int* __restrict__ c_dev,
+                                                    int steps, int* __restrict__ accepted) {
   __shared__ double sh[32];
+  const int c = *c_dev;
   double a = 0.0;
   for (int w = threadIdx.x; w < c; w += blockDim.x) {
     a += (double)accepted[w];
@@ -340,7 +295,8 @@ __global__ void __launch_bounds__(1024) k_slq_adapt(double* scalars, double inc,
   scalars[6] += prop;
 }
 
-// Copy retired points (local sorted order == global order when world == 1).
+// Copy retired points in the order of sidx (world == 1 with keepRetiredPoints: slots sorted by log-likelihood, i.e. the
+// global retirement order).
 __global__ void __launch_bounds__(256) k_slq_store(int c, int d, const int* __restrict__ sidx, const double* __restrict__ x,
                                                    double* __restrict__ dst) {
   const int lane = threadIdx.x & 31;
@@ -350,158 +306,58 @@ __global__ void __launch_bounds__(256) k_slq_store(int c, int d, const int* __re
   for (int j = lane; j < d; j += 32) dst[(size_t)w * d + j] = x[(size_t)s * d + j];
 }
 
-// ---- evidence accumulation -------------------------------------------------------------------------------------
-// One block per abscissa.  r[0..Kr) = retired log-likelihoods of this round in ascending order; the j-th of them was
-// retired with n0 - j points alive, so the prior mass shrinks by t = u^{1/(n0-j)} AFTER it has been assigned its X
-// (the reference assigns X = 1.0 to the very first retired point, QuadratureAbscissa.scala:64-73).
-// state: [0] logX assigned to the next point, [1] logX_{i-2}, [2] logX_{i-1}, [3] l_{i-1}, [4] pending count (0,1,2+),
-//        [5] running max m, [6] sum exp(term - m), [7] sum exp(term - m) * l
-__device__ __forceinline__ void lse_add(double& m, double& s, double& sl, double term, double l) {
-  if (!(term > -INFINITY)) return;
-  if (term > m) {
-    const double f = exp(m - term);
-    s = s * f + 1.0;
-    sl = sl * f + l;
-    m = term;
-  } else {
-    const double e = exp(term - m);
-    s += e;
-    sl += e * l;
-  }
+static SelectBuffers sel_buffers(thy_slq_s* h) {
+  SelectBuffers b{};
+  b.state = h->sel_state.ptr;
+  b.hist = h->sel_hist.ptr;
+  b.ticket = h->sel_ticket.ptr;
+  b.cursor = h->sel_cursor.ptr;
+  b.cnt = h->sel_cnt.ptr;
+  b.flags = h->flags.ptr;
+  b.sidx = h->sidx.ptr;
+  b.count = h->count_dev.ptr;
+  b.scalars = h->scalars.ptr;
+  return b;
 }
-__device__ __forceinline__ double log_half_gap(double lx_hi, double lx_lo) {
-  // ln( 1/2 (X_hi - X_lo) ),  X_hi >= X_lo given as logs
-  return log(0.5) + lx_hi + log(-expm1(lx_lo - lx_hi));
-}
-
-constexpr int EVT = 1024;  // threads of the evidence kernel
-
-__global__ void __launch_bounds__(EVT) k_slq_evidence(int Kr, long long n0, long long it0, uint64_t seed,
-                                                      const double* __restrict__ r, double* __restrict__ tmp_logx,
-                                                      long long tmp_stride, double* __restrict__ state, int finalize,
-                                                      double* __restrict__ out) {
-  __shared__ double wsum[EVT / 32];
-  __shared__ double carry;
-  __shared__ double red_m[EVT], red_s[EVT], red_sl[EVT];
-  const int a = blockIdx.x;
-  double* st = state + (size_t)a * 8;
-  double* lx = tmp_logx + (size_t)a * tmp_stride;
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  // pass 1: logX_j = logX_cur + sum_{k<j} ln t_k.  Each thread owns a contiguous segment: serial sum, block scan of
-  // the segment totals (warp shuffles), serial write-back.
-  {
-    const int S = (Kr + EVT - 1) / EVT;
-    const int j0 = tid * S < Kr ? tid * S : Kr, j1 = (j0 + S < Kr) ? j0 + S : Kr;
-    double local = 0.0;
-    for (int j = j0; j < j1; ++j) {
-      const RngDraw u = rng_uniform2(seed, (uint64_t)a, 0, RNG_SLQ_SHRINK, (uint64_t)(it0 + j));
-      const double lt = log(1.0 - u.u0) / (double)(n0 - j);   // ln u^{1/n}, u in (0,1]
-      lx[j] = lt;
-      local += lt;
-    }
-    double incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) wsum[wrp] = incl;
-    __syncthreads();
-    double base = st[0];
-    for (int w = 0; w < wrp; ++w) base += wsum[w];
-    double run = base + (incl - local);
-    for (int j = j0; j < j1; ++j) {
-      const double lt = lx[j];
-      lx[j] = run;
-      run += lt;
-    }
-    if (tid == EVT - 1) carry = run;   // logX assigned to the first point of the next round
-    __syncthreads();
-  }
-  // pass 2: finalise point j-1 once X_j is known: w_{j-1} = 1/2 (X_{j-2} - X_j)  (first ever point: 1/2 (X_0 - X_1))
-  double m = -INFINITY, s = 0.0, sl = 0.0;
-  const double pend = st[4];
-  for (int j = tid; j < Kr; j += EVT) {
-    double l_prev, lx_m2;
-    bool have_prev = true, first_ever = false;
-    if (j == 0) {
-      if (pend < 0.5) have_prev = false;
-      l_prev = st[3];
-      lx_m2 = st[1];
-      first_ever = pend < 1.5;   // pending point is the very first retired point: no X_{i-2}
-      if (first_ever) lx_m2 = st[2];  // use X_{i-1} itself: 1/2 (X_0 - X_1)
-    } else if (j == 1) {
-      l_prev = r[0];
-      lx_m2 = st[2];
-      if (pend < 0.5) { first_ever = true; lx_m2 = lx[0]; }
-    } else {
-      l_prev = r[j - 1];
-      lx_m2 = lx[j - 2];
-    }
-    if (have_prev) {
-      const double term = l_prev + log_half_gap(lx_m2, lx[j]);
-      lse_add(m, s, sl, term, l_prev);
-    }
-  }
-  red_m[tid] = m; red_s[tid] = s; red_sl[tid] = sl;
-  __syncthreads();
-  for (int o = EVT / 2; o > 0; o >>= 1) {
-    if (tid < o) {
-      double m2 = red_m[tid + o], s2 = red_s[tid + o], sl2 = red_sl[tid + o];
-      double m1 = red_m[tid], s1 = red_s[tid], sl1 = red_sl[tid];
-      if (m2 > m1) { const double f = exp(m1 - m2); s1 = s1 * f + s2; sl1 = sl1 * f + sl2; m1 = m2; }
-      else if (m2 > -INFINITY) { const double f = exp(m2 - m1); s1 += s2 * f; sl1 += sl2 * f; }
-      red_m[tid] = m1; red_s[tid] = s1; red_sl[tid] = sl1;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    double M = st[5], S = st[6], SL = st[7];
-    if (red_m[0] > -INFINITY) {
-      if (red_m[0] > M) { const double f = exp(M - red_m[0]); S = S * f + red_s[0]; SL = SL * f + red_sl[0]; M = red_m[0]; }
-      else { const double f = exp(red_m[0] - M); S += red_s[0] * f; SL += red_sl[0] * f; }
-    }
-    if (Kr > 0) {
-      // new pending point = last of this round
-      const double new_m1 = lx[Kr - 1];
-      const double new_m2 = (Kr >= 2) ? lx[Kr - 2] : st[2];
-      const double newpend = (Kr >= 2) ? 2.0 : (pend + 1.0);
-      st[1] = new_m2;
-      st[2] = new_m1;
-      st[3] = r[Kr - 1];
-      st[4] = newpend > 2.0 ? 2.0 : newpend;
-      st[0] = carry;
-    }
-    if (finalize && st[4] > 1.5) {
-      // last point: 1/2 (X_{N-2} - X_{N-1})
-      const double term = st[3] + log_half_gap(st[1], st[2]);
-      lse_add(M, S, SL, term, st[3]);
-      st[4] = 0.0;
-    }
-    st[5] = M; st[6] = S; st[7] = SL;
-    const double logZ = (S > 0.0) ? M + log(S) : -INFINITY;
-    out[a * 2 + 0] = logZ;
-    out[a * 2 + 1] = (S > 0.0) ? SL / S - logZ : 0.0;
-  }
+static EvidenceBuffers ev_buffers(thy_slq_s* h) {
+  EvidenceBuffers e{};
+  e.lt = h->ev_lt.ptr;
+  e.segsum = h->ev_segsum.ptr;
+  e.part = h->ev_part.ptr;
+  e.tickets = h->ev_tickets.ptr;
+  e.state = h->abs_state.ptr;
+  e.out = h->abs_out.ptr;
+  e.stride = std::max<long long>(h->K, h->P);
+  e.nseg_max = (int)((e.stride + 2047) / 2048);
+  return e;
 }
 
-static thy_status slq_sort_local(thy_slq_s* h) {
-  cudaStream_t s = h->model->stream;
-  THY_CUDA_CHECK(cudaMemcpyAsync(h->keys_in.ptr, h->ll.ptr, h->Pl * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->keys_in.ptr, h->keys_out.ptr, h->idx_in.ptr, h->idx_out.ptr, (int)h->Pl, 0, 64, s);
-  THY_TRY(h->cub_tmp.reserve(bytes));
-  THY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.ptr, bytes, h->keys_in.ptr, h->keys_out.ptr, h->idx_in.ptr,
-                                                 h->idx_out.ptr, (int)h->Pl, 0, 64, s));
-  return THY_OK;
-}
-
-static thy_status slq_sort_keys(thy_slq_s* h, const double* in, double* out, int n) {
-  cudaStream_t s = h->model->stream;
+// Ascending sort of n values (the round's K retired log-likelihoods; the whole pool once, at the drain).  This is the
+// one library call left in a round: cub's radix sort on the quadrature stream, off the critical path.
+static thy_status slq_sort_values(thy_slq_s* h, const double* in, double* out, int n, cudaStream_t s) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, n, 0, 64, s);
-  THY_TRY(h->cub_tmp.reserve(bytes));
+  if (bytes > h->cub_tmp.count) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return fail(THY_ERR_STATE, "SLQ: sort scratch must be sized before graph capture");
+    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+    THY_TRY(h->cub_tmp.reserve(bytes));
+  }
   THY_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(h->cub_tmp.ptr, bytes, in, out, n, 0, 64, s));
+  count_launch(3);
+  return THY_OK;
+}
+static thy_status slq_sort_pairs(thy_slq_s* h, const double* kin, double* kout, const int* vin, int* vout, int n,
+                                 cudaStream_t s) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, 64, s);
+  if (bytes > h->cub_tmp.count) {
+    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+    THY_CUDA_CHECK(cudaStreamSynchronize(h->side));
+    THY_TRY(h->cub_tmp.reserve(bytes));
+  }
+  THY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.ptr, bytes, kin, kout, vin, vout, n, 0, 64, s));
   count_launch(3);
   return THY_OK;
 }
@@ -513,156 +369,204 @@ static thy_status slq_eval(thy_slq_s* h, long long n, const double* X, double* l
   THY_TRY(launch_prior(m->prior_view, n, X, prior, nullptr, -1.0, m->stream));
   THY_CUDA_CHECK(cudaMemsetAsync(loglik, 0, (size_t)n * sizeof(double), m->stream));
   THY_TRY(eval_batch_dev(m, n, X, loglik, nullptr, true, true));
-  h->evals += n;
   return THY_OK;
 }
 
-static thy_status slq_evidence(thy_slq_s* h, const double* retired_sorted, int Kr, long long n0, int finalize,
-                               cudaStream_t s) {
-  const long long stride = std::max<long long>(h->K, h->P);
-  k_slq_evidence<<<h->A, EVT, 0, s>>>(Kr, n0, h->iterations, h->seed, retired_sorted, h->tmp_logx.ptr, stride,
-                                      h->abs_state.ptr, finalize, h->abs_out.ptr);
-  count_launch();
-  THY_CUDA_CHECK(cudaGetLastError());
-  return THY_OK;
-}
-
-// Selection phase of a round: proposal spread of the live pool, local sort, exchange of each rank's Kr smallest, merge,
-// threshold and local retire count, retired values appended.  Every launch has round-independent arguments (the
-// append position comes from h->ctl), so a full round's selection phase is captured once as a CUDA graph and replayed:
-// ~25 launches become one, which is what keeps 8 ranks from being host-launch bound.
-static thy_status slq_select_phase(thy_slq_s* h, int Kr, cudaStream_t s, bool tracing) {
-  const int d = h->d;
-  if (tracing) cudaEventRecord(h->tev[0], s);
-  const int nslab = 1184;   // 8 slabs per SM
-  k_slq_sigma_part<<<nslab, 256, 0, s>>>(h->Pl, d, h->x.ptr, h->sig_part.ptr, nslab);
-  k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(h->Pl, d, h->sig_part.ptr, nslab, h->sigma.ptr);
-  if (tracing) cudaEventRecord(h->tev[1], s);
-  THY_TRY(slq_sort_local(h));
-  if (tracing) cudaEventRecord(h->tev[2], s);
-  // each rank contributes its Kr smallest; the Kr globally smallest are retired
-  const double* merged = h->keys_out.ptr;
-  if (h->world > 1) {
-    THY_TRY(comm_all_gather_f64(h->comm, h->keys_out.ptr, h->cand_all.ptr, (size_t)Kr, s));
-    if (tracing) cudaEventRecord(h->tev[3], s);
-    k_slq_merge<<<(unsigned)ceil_div((long long)Kr * h->world, 256), 256, 0, s>>>(h->cand_all.ptr, Kr, h->world,
-                                                                                 h->cand_sorted.ptr);
-    merged = h->cand_sorted.ptr;
-  } else if (tracing) {
-    cudaEventRecord(h->tev[3], s);
-  }
-  k_slq_threshold<<<1, 32, 0, s>>>(merged, Kr, h->keys_out.ptr, h->cand_all.ptr, h->world, h->rank, h->scalars.ptr,
-                                   h->count_dev.ptr);
-  THY_CUDA_CHECK(cudaMemcpyAsync(h->host_c, h->count_dev.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-  k_slq_copy_retired<<<(unsigned)ceil_div(Kr, 256), 256, 0, s>>>(merged, Kr, h->ctl.ptr, h->ret_ll.ptr);
-  if (tracing) cudaEventRecord(h->tev[4], s);
-  THY_CUDA_CHECK(cudaGetLastError());
-  return THY_OK;
-}
-
-static thy_status slq_round(thy_slq_s* h, int Kr, int* out_local_count) {
+// One full round, enqueued on s (and the side stream, forked and joined): graph-capturable when the fused walk covers
+// the model.  tracing: CUDA events between the phases.
+static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool tracing) {
   thy_model_s* m = h->model;
-  cudaStream_t s = m->stream;
   const int d = h->d;
-  if (h->trace && h->rounds > 0) {   // the previous round's events have all completed or will by the sync below
-    cudaEventSynchronize(h->tev[5]);
-    for (int i = 0; i < 5; ++i) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]) == cudaSuccess) h->tsum[i] += ms;
+  const SelectBuffers sb = sel_buffers(h);
+  auto mark = [&](int i) { if (tracing) cudaEventRecord(h->tev[i], s); };
+  mark(0);
+  // ---- proposal spread of the live pool (strided subsample) ----
+  const long long nrows = std::min<long long>(h->Pl, 65536), row_stride = h->Pl / nrows;
+  const int nslab = (int)std::min<long long>(296, nrows);
+  k_slq_sigma_part<<<nslab, 256, 0, s>>>(nrows, row_stride, d, h->x.ptr, h->sig_part.ptr, nslab);
+  k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(nrows, d, h->sig_part.ptr, nslab, h->sigma.ptr);
+  count_launch(2);
+  mark(1);
+  // ---- every rank sees every log-likelihood: ONE collective per round ----
+  const double* keys = h->ll.ptr;
+  if (h->world > 1) {
+    THY_TRY(comm_all_gather_f64(h->comm, h->ll.ptr, h->keys_all.ptr, (size_t)h->Pl, s));
+    keys = h->keys_all.ptr;
+  }
+  mark(2);
+  // ---- threshold = K-th smallest; this rank's retirees ----
+  THY_TRY(slq_select_launch(sb, keys, h->Pl, h->world, h->rank, Kr, s));
+  mark(3);
+  THY_TRY(slq_gather_retired_values(sb, keys, h->P, Kr, h->vals_raw.ptr, s));   // before the walk overwrites retired slots
+  mark(4);
+  // ---- quadrature update beside the walk ----
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  THY_TRY(slq_sort_values(h, h->vals_raw.ptr, h->vals_sorted.ptr, Kr, h->side));
+  k_slq_copy_retired<<<(unsigned)ceil_div(Kr, 256), 256, 0, h->side>>>(h->vals_sorted.ptr, Kr, h->ctl.ptr, h->ret_ll.ptr);
+  THY_TRY(slq_evidence_launch(ev_buffers(h), h->A, Kr, h->P, h->K, LLONG_MAX, 0, h->ctl.ptr, h->seed, h->vals_sorted.ptr, 0,
+                              h->side));
+  k_slq_converge<<<1, 32, 0, h->side>>>(h->ctl.ptr, h->abs_out.ptr, h->A, Kr, (double)h->P, (long long)h->cfg.minIterationCount);
+  count_launch(2);
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->host_ao, h->abs_out.ptr, (size_t)h->A * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->side));
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->host_conv, h->ctl.ptr + 2, sizeof(long long), cudaMemcpyDeviceToHost, h->side));
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
+  // ---- retired positions in retirement order (single GPU, keepRetiredPoints): all Kr retirees are local ----
+  if (h->cfg.keepRetiredPoints && h->world == 1) {
+    k_slq_slot_keys<<<(unsigned)ceil_div(Kr, 256), 256, 0, s>>>(Kr, h->sidx.ptr, h->ll.ptr, h->Yp.ptr);
+    THY_TRY(slq_sort_pairs(h, h->Yp.ptr, h->tl.ptr, h->sidx.ptr, h->pair_out.ptr, Kr, s));
+    k_slq_store<<<(unsigned)ceil_div(Kr, 8), 256, 0, s>>>(Kr, d, h->pair_out.ptr, h->x.ptr, h->ret_x.ptr + (size_t)h->iterations * d);
+    count_launch(2);
+  }
+  // ---- replacement: constrained walks from survivors ----
+  if (h->fused_walk) {
+    THY_TRY(launch_slq_walk(m, Kr, h->count_dev.ptr, h->Pl, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->sidx.ptr, h->flags.ptr,
+                            h->x.ptr, h->ll.ptr, h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s));
+  } else {
+    int c = Kr;   // single GPU: every retiree is local
+    if (h->world > 1) {
+      THY_CUDA_CHECK(cudaMemcpyAsync(h->host_c, h->count_dev.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+      THY_CUDA_CHECK(cudaStreamSynchronize(s));
+      c = *h->host_c;
     }
-    h->tcount += 1;
+    if (c > h->K) return fail(THY_ERR_STATE, "SLQ: internal error, retire count exceeds the walker buffers");
+    if (c > 0) {
+      k_slq_spawn<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, h->Pl, d, h->seed, (uint64_t)h->rounds, h->rank, h->sidx.ptr,
+                                                          h->flags.ptr, h->x.ptr, h->ll.ptr, h->lpr.ptr, h->Y.ptr, h->yl.ptr,
+                                                          h->ypr.ptr, h->slot.ptr);
+      count_launch();
+      for (int step = 0; step < h->M; ++step) {
+        const uint64_t gstep = (uint64_t)h->rounds * (uint64_t)h->M + step;
+        k_slq_propose<<<(unsigned)ceil_div((long long)c * d, 256), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr,
+                                                                                 h->sigma.ptr, h->scalars.ptr, h->Yp.ptr);
+        THY_TRY(slq_eval(h, c, h->Yp.ptr, h->tl.ptr, h->tpr.ptr));
+        k_slq_accept<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
+                                                             h->Yp.ptr, h->tl.ptr, h->tpr.ptr, h->scalars.ptr, h->accepted.ptr);
+        count_launch(2);
+      }
+      k_slq_commit<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->slot.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr, h->x.ptr,
+                                                           h->ll.ptr, h->lpr.ptr);
+      count_launch();
+    }
   }
+  k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability,
+                                 h->count_dev.ptr, h->M, h->accepted.ptr);
+  count_launch();
+  mark(5);
+  THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
+  mark(6);
+  k_slq_advance<<<1, 1, 0, s>>>(h->ctl.ptr, Kr);
+  count_launch();
+  mark(7);
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
+}
+
+static thy_status slq_round(thy_slq_s* h, int Kr) {
+  cudaStream_t s = h->model->stream;
   if (h->iterations + Kr > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
-  const auto ht0 = std::chrono::steady_clock::now();
-  *h->host_it = h->iterations;   // the previous round's copy of this word completed before its sync returned
-  THY_CUDA_CHECK(cudaMemcpyAsync(h->ctl.ptr, h->host_it, sizeof(long long), cudaMemcpyHostToDevice, s));
-  const bool graphable = h->use_graph && !h->trace && s != 0 && Kr == h->K && h->rounds > 0;   // round 0 sizes the sort scratch
-  if (h->select_graph && h->select_graph_stream != s) {   // the model was moved to another stream: re-capture
-    cudaGraphExecDestroy(h->select_graph);
-    h->select_graph = nullptr;
+  const bool graphable = h->use_graph && !h->trace && s != 0 && Kr == h->K && h->fused_walk && h->sort_sized &&
+                         !(h->cfg.keepRetiredPoints && h->world == 1);
+  if (h->graph && h->graph_stream != s) {   // the model was moved to another stream: re-capture
+    cudaGraphExecDestroy(h->graph);
+    h->graph = nullptr;
   }
-  if (graphable && !h->select_graph) {
-    h->select_graph_stream = s;
+  if (graphable && !h->graph) {
     cudaGraph_t g = nullptr;
+    const uint64_t before = g_kernel_launches.load();
     THY_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    thy_status st = slq_select_phase(h, Kr, s, false);
-    cudaError_t ce = cudaStreamEndCapture(s, &g);
+    const thy_status st = slq_round_enqueue(h, Kr, s, false);
+    const cudaError_t ce = cudaStreamEndCapture(s, &g);
+    h->graph_launches = g_kernel_launches.load() - before;
+    g_kernel_launches.store(before);   // captured, not executed
     if (st != THY_OK || ce != cudaSuccess || !g) {
       if (g) cudaGraphDestroy(g);
       cudaGetLastError();
       h->use_graph = false;   // capture unsupported here (e.g. a collective library without graph support): plain launches
     } else {
-      ce = cudaGraphInstantiate(&h->select_graph, g, 0);
+      const cudaError_t ci = cudaGraphInstantiate(&h->graph, g, 0);
       cudaGraphDestroy(g);
-      if (ce != cudaSuccess) {
+      if (ci != cudaSuccess) {
         cudaGetLastError();
-        h->select_graph = nullptr;
+        h->graph = nullptr;
         h->use_graph = false;
+      } else {
+        h->graph_stream = s;
       }
     }
   }
-  const int select_launches = 2 + 11 + (h->world > 1 ? 2 : 0) + 2;
-  if (graphable && h->select_graph) {
-    THY_CUDA_CHECK(cudaGraphLaunch(h->select_graph, s));
+  if (graphable && h->graph) {
+    THY_CUDA_CHECK(cudaGraphLaunch(h->graph, s));
+    count_launch(h->graph_launches);
   } else {
-    THY_TRY(slq_select_phase(h, Kr, s, h->trace));
+    THY_TRY(slq_round_enqueue(h, Kr, s, h->trace));
+    h->sort_sized = true;
   }
-  count_launch(select_launches);
-  // the evidence update only needs the retired values: it runs on the side stream while the walk replaces the points
-  THY_CUDA_CHECK(cudaEventRecord(h->ev_retired, s));
-  THY_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_retired, 0));
-  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, Kr, h->P, 0, h->side));
-  THY_CUDA_CHECK(cudaMemcpyAsync(h->host_ao, h->abs_out.ptr, (size_t)h->A * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->side));
-  THY_CUDA_CHECK(cudaEventRecord(h->ev_evidence, h->side));
-  const auto ht1 = std::chrono::steady_clock::now();
-  THY_CUDA_CHECK(cudaStreamSynchronize(s));
-  const auto ht2 = std::chrono::steady_clock::now();
-  const int c = *h->host_c;
-  if (c > h->K) return fail(THY_ERR_STATE, "SLQ: internal error, retire count exceeds the walker buffers");
-  if (c >= h->Pl) return fail(THY_ERR_STATE, "SLQ: a rank lost all of its live points in one round; lower sampleParallelism");
-  if (h->cfg.keepRetiredPoints && h->world == 1 && c > 0) {
-    k_slq_store<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->idx_out.ptr, h->x.ptr, h->ret_x.ptr + (size_t)h->iterations * d);
-    count_launch();
-  }
-  if (c > 0) {
-    if (h->fused_walk) {
-      THY_TRY(launch_slq_walk(m, c, h->Pl, h->M, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr, h->x.ptr, h->ll.ptr,
-                              h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s));
-      h->evals += (long long)c * h->M;
-    } else {
-    k_slq_spawn<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, h->Pl, d, h->seed, (uint64_t)h->rounds, h->rank, h->idx_out.ptr,
-                                                        h->x.ptr, h->ll.ptr, h->lpr.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
-                                                        h->slot.ptr);
-    count_launch();
-    for (int step = 0; step < h->M; ++step) {
-      const uint64_t gstep = (uint64_t)h->rounds * (uint64_t)h->M + step;
-      k_slq_propose<<<(unsigned)ceil_div((long long)c * d, 256), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr,
-                                                                               h->sigma.ptr, h->scalars.ptr, h->Yp.ptr);
-      THY_TRY(slq_eval(h, c, h->Yp.ptr, h->tl.ptr, h->tpr.ptr));
-      k_slq_accept<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->seed, gstep, h->rank, h->Y.ptr, h->yl.ptr, h->ypr.ptr,
-                                                           h->Yp.ptr, h->tl.ptr, h->tpr.ptr, h->scalars.ptr, h->accepted.ptr);
-      count_launch(2);
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_round[h->rounds % 3], s));
+  if (h->trace) {
+    THY_CUDA_CHECK(cudaEventSynchronize(h->tev[7]));
+    for (int i = 0; i < 7; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]) == cudaSuccess) h->tsum[i] += ms;
     }
-    k_slq_commit<<<(unsigned)ceil_div(c, 8), 256, 0, s>>>(c, d, h->slot.ptr, h->Y.ptr, h->yl.ptr, h->ypr.ptr, h->x.ptr,
-                                                         h->ll.ptr, h->lpr.ptr);
-    count_launch();
-    }
-    k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability, c, h->M,
-                                   h->accepted.ptr);
-    count_launch();
+    h->tcount += 1;
   }
-  if (h->trace) cudaEventRecord(h->tev[5], s);
-  if (h->htrace) {
-    const auto ht3 = std::chrono::steady_clock::now();
-    h->hsum[0] += std::chrono::duration<double>(ht1 - ht0).count();
-    h->hsum[1] += std::chrono::duration<double>(ht2 - ht1).count();
-    h->hsum[2] += std::chrono::duration<double>(ht3 - ht2).count();
-    h->hcount += 1;
-  }
-  THY_CUDA_CHECK(cudaGetLastError());
   h->iterations += Kr;
   h->rounds += 1;
-  if (out_local_count) *out_local_count = c;
+  h->evals += (long long)Kr * h->M;
+  return THY_OK;
+}
+
+// Live phase: rounds of "retire the K lowest, replace them above the threshold" until the reference's convergence test
+// (SlqEngine.scala:249-262) or maxIterationCount.  The host stays at most two rounds ahead of the device: before it
+// enqueues round r it waits for round r - 2 and reads the device's write-once "first converged round" word.  Stopping
+// once that word is <= r - 2 makes every rank run exactly (first converged round + 2) rounds, whatever the host timing.
+static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* converged) {
+  *converged = false;
+  for (long long r = 0; r < max_rounds; ++r) {
+    const long long remaining = (long long)h->cfg.maxIterationCount - h->iterations;
+    if (remaining <= 0) {
+      *converged = true;
+      break;
+    }
+    if (h->rounds >= 2) {
+      THY_CUDA_CHECK(cudaEventSynchronize(h->ev_round[(h->rounds - 2) % 3]));
+      const long long fc = *(volatile long long*)h->host_conv;
+      if (fc >= 0 && fc <= h->rounds - 2) {
+        *converged = true;
+        break;
+      }
+    }
+    THY_TRY(slq_round(h, (int)std::min<long long>(h->K, remaining)));
+  }
+  return THY_OK;
+}
+
+__global__ void __launch_bounds__(256) k_slq_gather_rows(int n, int d, const long long* __restrict__ idx,
+                                                         const double* __restrict__ src, double* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n) return;
+  const long long s = idx[w];
+  for (int j = lane; j < d; j += 32) dst[(size_t)w * d + j] = src[(size_t)s * d + j];
+}
+
+// ln X of abscissa a for the retired points [0, n) into host memory (chunked through the quadrature scratch).
+static thy_status slq_export_logx(thy_slq_s* h, int a, long long n, double* out_host) {
+  cudaStream_t s = h->model->stream;
+  const EvidenceBuffers e = ev_buffers(h);
+  const long long live = h->live_iterations >= 0 ? h->live_iterations : LLONG_MAX;
+  const int chunk = (int)std::min<long long>(e.stride, 1 << 20);
+  DevBuf<double> carry, buf;
+  THY_TRY(carry.reserve(1));
+  THY_TRY(buf.reserve((size_t)chunk));
+  THY_CUDA_CHECK(cudaMemsetAsync(carry.ptr, 0, sizeof(double), s));
+  for (long long i0 = 0; i0 < n; i0 += chunk) {
+    const int cnt = (int)std::min<long long>(chunk, n - i0);
+    THY_TRY(slq_logx_launch(e, a, i0, cnt, h->P, h->K, live, h->seed, carry.ptr, buf.ptr, s));
+    THY_CUDA_CHECK(cudaMemcpyAsync(out_host + i0, buf.ptr, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
   return THY_OK;
 }
 
@@ -700,50 +604,52 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   h->A = cfg->abscissaNumber;
   h->M = cfg->constrainedWalkSteps > 0 ? cfg->constrainedWalkSteps : 20;
   int K = cfg->sampleParallelism > 0 ? cfg->sampleParallelism : 1;
-  // every rank contributes its K smallest and must keep survivors to spawn from: K <= half of a rank's pool (a rank
-  // holds ~K / world of a round's retirees; one that would lose its whole pool is reported as an error)
+  // the K globally lowest may all sit on one rank, which must keep survivors to spawn from: K <= half of a rank's pool
   K = (int)std::min<long long>(K, std::max<long long>(1, h->Pl / 2));
   h->K = K;
   h->ret_capacity = (long long)cfg->maxIterationCount + K + h->P;
   const int d = h->d;
   const long long Pl = h->Pl;
+  const long long KP = std::max<long long>(K, h->P);
+  const int spr = slq_select_slices(Pl);
+  const int nseg_max = (int)((KP + 2047) / 2048);
   thy_status st = THY_OK;
   auto chk = [&](thy_status s2) { if (st == THY_OK) st = s2; };
   chk(h->x.reserve((size_t)Pl * d)); chk(h->ll.reserve(Pl)); chk(h->lpr.reserve(Pl));
-  chk(h->keys_in.reserve(Pl)); chk(h->keys_out.reserve(Pl)); chk(h->idx_in.reserve(Pl)); chk(h->idx_out.reserve(Pl));
-  chk(h->cand_all.reserve((size_t)std::max<long long>((long long)K * world, h->P)));
-  chk(h->cand_sorted.reserve((size_t)std::max<long long>((long long)K * world, h->P)));
-  chk(h->Y.reserve((size_t)K * d)); chk(h->Yp.reserve((size_t)K * d)); chk(h->yl.reserve(K)); chk(h->ypr.reserve(K));
+  if (world > 1) chk(h->keys_all.reserve((size_t)h->P));
+  chk(h->sel_state.reserve(1)); chk(h->sel_hist.reserve(2048)); chk(h->sel_ticket.reserve(1)); chk(h->sel_cursor.reserve(1));
+  chk(h->sel_cnt.reserve((size_t)spr * world)); chk(h->flags.reserve(Pl)); chk(h->sidx.reserve(K)); chk(h->count_dev.reserve(1));
+  chk(h->vals_raw.reserve((size_t)KP)); chk(h->vals_sorted.reserve((size_t)KP));
+  chk(h->pair_in.reserve((size_t)std::max<long long>(K, Pl))); chk(h->pair_out.reserve((size_t)std::max<long long>(K, Pl)));
+  chk(h->Y.reserve((size_t)K * d)); chk(h->Yp.reserve((size_t)K * std::max(d, 1))); chk(h->yl.reserve(K)); chk(h->ypr.reserve(K));
   chk(h->tl.reserve(K)); chk(h->tpr.reserve(K)); chk(h->slot.reserve(K)); chk(h->accepted.reserve(K));
-  chk(h->sigma.reserve(d)); chk(h->sig_part.reserve((size_t)1184 * 2 * d));
-  chk(h->scalars.reserve(8)); chk(h->count_dev.reserve(1));
-  chk(h->tmp_logx.reserve((size_t)h->A * std::max<long long>(K, h->P)));
-  chk(h->abs_state.reserve((size_t)h->A * 8)); chk(h->abs_out.reserve((size_t)h->A * 2));
+  chk(h->sigma.reserve(d)); chk(h->sig_part.reserve((size_t)296 * 2 * d));
+  chk(h->scalars.reserve(8));
+  chk(h->ev_lt.reserve((size_t)h->A * KP)); chk(h->ev_segsum.reserve((size_t)h->A * nseg_max));
+  chk(h->ev_part.reserve((size_t)h->A * nseg_max * 3)); chk(h->ev_tickets.reserve(h->A));
+  chk(h->abs_state.reserve((size_t)h->A * EV_STATE)); chk(h->abs_out.reserve((size_t)h->A * 2));
   chk(h->ret_ll.reserve((size_t)h->ret_capacity));
+  chk(h->ctl.reserve(3));
   if (cfg->keepRetiredPoints) {
     if (world != 1) chk(fail(THY_ERR_UNSUPPORTED, "keepRetiredPoints is single-GPU only in this version"));
     chk(h->ret_x.reserve((size_t)h->ret_capacity * d));
   }
   cudaStream_t s = m->stream;
   if (st == THY_OK) {
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_retired, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_evidence, cudaEventDisableTiming) != cudaSuccess ||
-        cudaMallocHost(&h->host_ao, (size_t)h->A * 2 * sizeof(double)) != cudaSuccess ||
-        cudaMallocHost(&h->host_c, sizeof(int)) != cudaSuccess ||
-        cudaMallocHost(&h->host_it, sizeof(long long)) != cudaSuccess ||
-        cudaEventRecord(h->ev_evidence, h->side) != cudaSuccess)
-      st = fail(THY_ERR_CUDA, "SLQ side stream setup failed");
+    bool ok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMallocHost(&h->host_ao, (size_t)h->A * 2 * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost(&h->host_c, sizeof(int)) == cudaSuccess &&
+              cudaMallocHost(&h->host_conv, sizeof(long long)) == cudaSuccess;
+    for (auto& e : h->ev_round) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) st = fail(THY_ERR_CUDA, "SLQ stream / event setup failed");
+    else *h->host_conv = -1;
     h->fused_walk = !cfg->disableFusedWalk && slq_walk_supported(m);
-    chk(h->ctl.reserve(1));
     const char* ng = std::getenv("THY_SLQ_GRAPH");
     h->use_graph = !(ng && ng[0] == '0');
     const char* tr = std::getenv("THY_SLQ_TRACE");
-    h->trace = tr && tr[0] == '1';
-    h->htrace = tr && tr[0] == '2';
-    if (h->trace)
-      for (auto& e : h->tev)
-        if (cudaEventCreate(&e) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ trace events");
+    if (tr && tr[0] == '1') chk(thy_slq_set_trace(h, 1));
   }
   if (st == THY_OK) {
     // initial pool: prior draws (+ seeds in the first slots, SlqEngine.scala:384-389,409)
@@ -756,15 +662,22 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   }
   if (st == THY_OK) {
     chk(slq_eval(h, Pl, h->x.ptr, h->ll.ptr, h->lpr.ptr));
-    k_iota<<<(unsigned)ceil_div(Pl, 256), 256, 0, s>>>((int)Pl, h->idx_in.ptr);
     std::vector<double> sc = {0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (st == THY_OK && cudaMemsetAsync(h->accepted.ptr, 0, (size_t)K * sizeof(int), s) != cudaSuccess)
-      st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
+    bool ok = cudaMemsetAsync(h->accepted.ptr, 0, (size_t)K * sizeof(int), s) == cudaSuccess &&
+              cudaMemsetAsync(h->sel_hist.ptr, 0, 2048 * sizeof(unsigned int), s) == cudaSuccess &&
+              cudaMemsetAsync(h->sel_ticket.ptr, 0, sizeof(unsigned int), s) == cudaSuccess &&
+              cudaMemsetAsync(h->sel_cursor.ptr, 0, sizeof(unsigned int), s) == cudaSuccess &&
+              cudaMemsetAsync(h->sel_state.ptr, 0, sizeof(SelectState), s) == cudaSuccess &&
+              cudaMemsetAsync(h->flags.ptr, 0, (size_t)Pl, s) == cudaSuccess &&
+              cudaMemsetAsync(h->count_dev.ptr, 0, sizeof(int), s) == cudaSuccess &&
+              cudaMemsetAsync(h->ev_tickets.ptr, 0, (size_t)h->A * sizeof(unsigned int), s) == cudaSuccess;
+    if (!ok) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
     chk(h->scalars.upload(sc, s));
-    std::vector<double> stt((size_t)h->A * 8, 0.0);
-    for (int a = 0; a < h->A; ++a) stt[(size_t)a * 8 + 5] = -INFINITY;
+    std::vector<double> stt((size_t)h->A * EV_STATE, 0.0);
+    for (int a = 0; a < h->A; ++a) stt[(size_t)a * EV_STATE + 5] = -INFINITY;
     chk(h->abs_state.upload(stt, s));
-    count_launch();
+    std::vector<long long> ctl = {0, 0, -1};
+    chk(h->ctl.upload(ctl, s));
     if (cudaStreamSynchronize(s) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
   }
   if (st != THY_OK) {
@@ -776,39 +689,32 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
 }
 
 thy_status thy_slq_destroy(thy_slq_t h) {
+  if (h && h->trace && h->tcount > 0 && std::getenv("THY_SLQ_TRACE")) {
+    std::fprintf(stderr, "[thy slq trace] rank %d: %lld rounds; us/round:", h->rank, h->tcount);
+    for (int i = 0; i < 7; ++i) std::fprintf(stderr, " %s %.1f%s", kPhaseNames[i], 1e3 * h->tsum[i] / h->tcount, i < 6 ? "," : "\n");
+  }
   delete h;
   return THY_OK;
 }
 
-// Live phase: rounds of "retire the K lowest, replace them above the threshold" until the reference's convergence test
-// (SlqEngine.scala:249-262: iterations > minIterationCount && iterations >= 10 P H) or maxIterationCount.
-static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* converged) {
-  cudaStream_t s = h->model->stream;
-  std::vector<double> ao((size_t)h->A * 2);
-  *converged = false;
-  for (long long r = 0; r < max_rounds; ++r) {
-    const long long remaining = (long long)h->cfg.maxIterationCount - h->iterations;
-    if (remaining <= 0) { *converged = true; break; }
-    const int Kr = (int)std::min<long long>(h->K, remaining);
-    int c = 0;
-    THY_TRY(slq_round(h, Kr, &c));
-    // the side stream finishes the evidence update long before the walk ends: the host decides on convergence and
-    // queues the next round's sort while the walk is still running
-    const auto hw0 = std::chrono::steady_clock::now();
-    THY_CUDA_CHECK(cudaEventSynchronize(h->ev_evidence));
-    if (h->htrace) h->hsum[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - hw0).count();
-    double hmax = -INFINITY;
-    for (int a = 0; a < h->A; ++a) hmax = std::max(hmax, h->host_ao[(size_t)a * 2 + 1]);
-    if (h->iterations > h->cfg.minIterationCount && std::isfinite(hmax) &&
-        (double)h->iterations >= 10.0 * (double)h->P * hmax) {
-      *converged = true;
-      break;
-    }
-  }
+thy_status thy_slq_set_trace(thy_slq_t h, int enable) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (enable && !h->tev[0])
+    for (auto& e : h->tev)
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(THY_ERR_CUDA, "SLQ trace events");
+  h->trace = enable != 0;
   return THY_OK;
 }
 
-extern "C" thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged) {
+thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_rounds) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  for (int i = 0; i < 7; ++i)
+    if (out_us) out_us[i] = h->tcount > 0 ? 1e3 * h->tsum[i] / h->tcount : 0.0;
+  if (out_rounds) *out_rounds = h->tcount;
+  return THY_OK;
+}
+
+thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged) {
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (h->finished) return fail(THY_ERR_STATE, "the simulation has already been drained");
   bool conv = false;
@@ -817,7 +723,7 @@ extern "C" thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_con
   return THY_OK;
 }
 
-extern "C" thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
+thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (h->finished) {
     if (out_stats) *out_stats = h->stats;
@@ -827,30 +733,34 @@ extern "C" thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   std::vector<double> ao((size_t)h->A * 2);
   bool conv = false;
   THY_TRY(slq_live_phase(h, (long long)1 << 60, &conv));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
   // drainSamplePool (SlqEngine.scala:171-180): the remaining live points in ascending order
-  THY_TRY(slq_sort_local(h));
-  const double* merged = h->keys_out.ptr;
+  const double* keys = h->ll.ptr;
   if (h->world > 1) {
-    THY_TRY(comm_all_gather_f64(h->comm, h->keys_out.ptr, h->cand_all.ptr, (size_t)h->Pl, s));
-    THY_TRY(slq_sort_keys(h, h->cand_all.ptr, h->cand_sorted.ptr, (int)h->P));
-    merged = h->cand_sorted.ptr;
+    THY_TRY(comm_all_gather_f64(h->comm, h->ll.ptr, h->keys_all.ptr, (size_t)h->Pl, s));
+    keys = h->keys_all.ptr;
   }
   if (h->iterations + h->P > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
-  THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, merged, (size_t)h->P * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (h->cfg.keepRetiredPoints && h->world == 1) {
-    k_slq_store<<<(unsigned)ceil_div(h->Pl, 8), 256, 0, s>>>((int)h->Pl, h->d, h->idx_out.ptr, h->x.ptr,
+    k_iota<<<(unsigned)ceil_div(h->Pl, 256), 256, 0, s>>>((int)h->Pl, h->pair_in.ptr);
+    THY_TRY(slq_sort_pairs(h, keys, h->vals_sorted.ptr, h->pair_in.ptr, h->pair_out.ptr, (int)h->P, s));
+    k_slq_store<<<(unsigned)ceil_div(h->Pl, 8), 256, 0, s>>>((int)h->Pl, h->d, h->pair_out.ptr, h->x.ptr,
                                                             h->ret_x.ptr + (size_t)h->iterations * h->d);
-    count_launch();
+    count_launch(2);
+  } else {
+    THY_TRY(slq_sort_values(h, keys, h->vals_sorted.ptr, (int)h->P, s));
   }
-  THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_evidence, 0));   // the last round's evidence update (side stream)
-  THY_TRY(slq_evidence(h, h->ret_ll.ptr + h->iterations, (int)h->P, h->P, 1, s));
-  const long long live_iterations = h->iterations;
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + h->iterations, h->vals_sorted.ptr, (size_t)h->P * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s));
+  h->live_iterations = h->iterations;
+  THY_TRY(slq_evidence_launch(ev_buffers(h), h->A, (int)h->P, h->P, h->K, h->live_iterations, h->iterations, nullptr, h->seed,
+                              h->vals_sorted.ptr, 1, s));
   h->iterations += h->P;
   std::vector<double> sc(8);
   THY_CUDA_CHECK(cudaMemcpyAsync(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
   THY_CUDA_CHECK(cudaMemcpyAsync(sc.data(), h->scalars.ptr, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
   double minl = 0.0;
-  THY_CUDA_CHECK(cudaMemcpyAsync(&minl, h->ret_ll.ptr + live_iterations, sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaMemcpyAsync(&minl, h->ret_ll.ptr + h->live_iterations, sizeof(double), cudaMemcpyDeviceToHost, s));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
   double mean = 0.0, m2 = 0.0, hm = 0.0;
   for (int a = 0; a < h->A; ++a) {
@@ -860,7 +770,7 @@ extern "C" thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   mean /= h->A;
   hm /= h->A;
   for (int a = 0; a < h->A; ++a) m2 += (ao[(size_t)a * 2] - mean) * (ao[(size_t)a * 2] - mean);
-  h->stats.iterations = live_iterations;
+  h->stats.iterations = h->live_iterations;
   h->stats.total_retired = h->iterations;
   h->stats.rounds = h->rounds;
   h->stats.log_evidence_mean = mean;
@@ -883,6 +793,17 @@ thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, i
     THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
     THY_CUDA_CHECK(cudaMemcpy(out_loglik, h->ret_ll.ptr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
   }
+  if (out_count) *out_count = h->iterations;
+  return THY_OK;
+}
+
+/* ln X_i of one simulated abscissa for the retired points, in retirement order (QuadratureAbscissa.scala:33-73): the
+ * prior-mass simulation is replayed on the device from the counter RNG, so nothing had to be stored during the run. */
+thy_status thy_slq_retired_log_x(thy_slq_t h, int abscissa, int64_t max_count, double* out_log_x, int64_t* out_count) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (abscissa < 0 || abscissa >= h->A) return fail(THY_ERR_INVALID_ARGUMENT, "abscissa index out of range");
+  const long long n = std::min<long long>(max_count, h->iterations);
+  if (out_log_x && n > 0) THY_TRY(slq_export_logx(h, abscissa, n, out_log_x));
   if (out_count) *out_count = h->iterations;
   return THY_OK;
 }
@@ -911,47 +832,111 @@ thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, doubl
   return THY_OK;
 }
 
-/* Posterior resampling of retired points (SamplingSimulation.scala:41-101) with weight w_i L_i under the expected
- * abscissa E[ln X_i] = -sum 1/n_k.  Requires keepRetiredPoints (single GPU). */
+/* integrate (SlqEngine.scala:460-466 -> QuadratureIntegrator.getIntegrationStats, QuadratureIntegrator.scala:64-83):
+ * per simulated abscissa a,  I_a = sum_i w_{a,i} f(exp(l_i - shift)),  Z_a = sum_i w_{a,i} exp(l_i - shift)  with the
+ * trapezoid weights of that abscissa; the reference returns the mean over a of  I_a / Z_a - ln Z_a  (literally what
+ * getIntegrationStats computes) -> out_reference_statistic; the plain quadrature mean over a of I_a -> out_integral.
+ * log_shift: NaN = the reference's (max l + min l) / 2 (its BigDecimal arithmetic cannot overflow; in fp64 that shift can,
+ * so callers may pass e.g. max l).  The integrand is a host callback, as the reference's is a JVM closure. */
+thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* user, double log_shift,
+                             double* out_reference_statistic, double* out_integral, double* out_per_abscissa_integral) {
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  if (!integrand) return fail(THY_ERR_INVALID_ARGUMENT, "null integrand");
+  if (!h->finished) return fail(THY_ERR_STATE, "run the simulation first (rebuildSampleSimulation)");
+  const long long N = h->iterations;
+  std::vector<double> l((size_t)N), lx((size_t)N);
+  THY_CUDA_CHECK(cudaMemcpy(l.data(), h->ret_ll.ptr, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+  double lmax = -INFINITY, lmin = INFINITY;
+  for (double v : l) {
+    if (v > lmax) lmax = v;
+    if (v < lmin && v > -INFINITY) lmin = v;
+  }
+  const double shift = std::isnan(log_shift) ? 0.5 * (lmax + lmin) : log_shift;
+  std::vector<double> fv((size_t)N), ev((size_t)N);
+  for (long long i = 0; i < N; ++i) {
+    ev[(size_t)i] = std::exp(l[(size_t)i] - shift);
+    fv[(size_t)i] = integrand(ev[(size_t)i], user);
+  }
+  long double stat = 0.0L, integ = 0.0L;
+  for (int a = 0; a < h->A; ++a) {
+    THY_TRY(slq_export_logx(h, a, N, lx.data()));
+    long double Ia = 0.0L, Za = 0.0L;
+    for (long long i = 0; i < N; ++i) {
+      const double xm = std::exp(lx[(size_t)(i == 0 ? 0 : i - 1)]), xp = std::exp(lx[(size_t)(i + 1 < N ? i + 1 : i)]);
+      const double w = 0.5 * (xm - xp);
+      Ia += (long double)w * fv[(size_t)i];
+      Za += (long double)w * ev[(size_t)i];
+    }
+    if (out_per_abscissa_integral) out_per_abscissa_integral[a] = (double)Ia;
+    stat += Ia / Za - logl(Za);
+    integ += Ia;
+  }
+  if (out_reference_statistic) *out_reference_statistic = (double)(stat / h->A);
+  if (out_integral) *out_integral = (double)(integ / h->A);
+  return THY_OK;
+}
+
+/* sample(n) (SlqEngine.scala:452-469 -> SamplingSimulation.scala:41-101): every draw picks one of the simulated
+ * abscissas uniformly, then a retired point with probability proportional to that abscissa's trapezoid area
+ * 1/2 (L_i + L_next)(X_i - X_next) (the innermost point: L X).  The staircases are built on the host from the exported
+ * ln X; the chosen points are gathered on the device and copied back in ONE transfer.  Requires keepRetiredPoints. */
 thy_status thy_slq_sample(thy_slq_t h, int n, uint64_t rng_seed, double* out_samples) {
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->finished) return fail(THY_ERR_STATE, "run the simulation first (rebuildSampleSimulation)");
   if (!h->cfg.keepRetiredPoints || h->world != 1) return fail(THY_ERR_UNSUPPORTED, "retired points were not kept");
   if (n <= 0 || !out_samples) return fail(THY_ERR_INVALID_ARGUMENT, "bad arguments");
   const long long N = h->iterations;
-  std::vector<double> l((size_t)N);
+  std::vector<double> l((size_t)N), lx((size_t)N), cdf((size_t)N);
   THY_CUDA_CHECK(cudaMemcpy(l.data(), h->ret_ll.ptr, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
-  // expected log X: live phase shrinks by 1/(P - j) within rounds of K, drain by 1/(P - j)
-  std::vector<double> lx((size_t)N);
-  double cur = 0.0;
-  const long long live = h->stats.iterations;
-  for (long long i = 0; i < N; ++i) {
-    lx[(size_t)i] = cur;
-    const long long j = (i < live) ? (i % h->K) : (i - live);
-    cur -= 1.0 / (double)(h->P - j);
-  }
-  std::vector<double> lw((size_t)N);
-  double mx = -INFINITY;
-  for (long long i = 0; i < N; ++i) {
-    const double hi = (i == 0) ? lx[0] : lx[(size_t)i - 1];
-    const double lo = (i + 1 < N) ? lx[(size_t)i + 1] : lx[(size_t)i];
-    const double gap = std::log(0.5) + hi + std::log(-std::expm1(lo - hi));
-    lw[(size_t)i] = l[(size_t)i] + gap;
-    mx = std::max(mx, lw[(size_t)i]);
-  }
-  std::vector<double> cdf((size_t)N);
-  double run = 0.0;
-  for (long long i = 0; i < N; ++i) {
-    run += std::exp(lw[(size_t)i] - mx);
-    cdf[(size_t)i] = run;
-  }
+  // draws grouped by abscissa
+  std::vector<int> which((size_t)n);
+  std::vector<double> uu((size_t)n);
   for (int k = 0; k < n; ++k) {
     const RngDraw u = rng_uniform2(rng_seed, (uint64_t)k, 0, RNG_SLQ_PICK, 0xFFFFFFFFull);
-    const double target = u.u0 * run;
-    const long long idx = std::min<long long>(N - 1, std::upper_bound(cdf.begin(), cdf.end(), target) - cdf.begin());
-    THY_CUDA_CHECK(cudaMemcpy(out_samples + (size_t)k * h->d, h->ret_x.ptr + (size_t)idx * h->d, h->d * sizeof(double),
-                              cudaMemcpyDeviceToHost));
+    int a = (int)(u.u1 * h->A);
+    which[(size_t)k] = a >= h->A ? h->A - 1 : a;
+    uu[(size_t)k] = u.u0;
   }
+  std::vector<long long> idx((size_t)n, 0);
+  for (int a = 0; a < h->A; ++a) {
+    bool used = false;
+    for (int k = 0; k < n && !used; ++k) used = which[(size_t)k] == a;
+    if (!used) continue;
+    THY_TRY(slq_export_logx(h, a, N, lx.data()));
+    // log weight of point i: trapezoid between X_i and X_{i+1} (X_N = 0)
+    double mx = -INFINITY;
+    for (long long i = 0; i < N; ++i) {
+      double lw;
+      if (i + 1 < N) {
+        const double la = l[(size_t)i], lb = l[(size_t)i + 1];
+        const double lsum = lb + std::log1p(std::exp(la - lb));   // ln(L_i + L_{i+1}), l ascending
+        lw = std::log(0.5) + lsum + lx[(size_t)i] + std::log(-std::expm1(lx[(size_t)i + 1] - lx[(size_t)i]));
+      } else {
+        lw = l[(size_t)i] + lx[(size_t)i];
+      }
+      cdf[(size_t)i] = lw;
+      if (lw > mx) mx = lw;
+    }
+    double run = 0.0;
+    for (long long i = 0; i < N; ++i) {
+      run += std::exp(cdf[(size_t)i] - mx);
+      cdf[(size_t)i] = run;
+    }
+    for (int k = 0; k < n; ++k) {
+      if (which[(size_t)k] != a) continue;
+      const double target = uu[(size_t)k] * run;
+      idx[(size_t)k] = std::min<long long>(N - 1, std::upper_bound(cdf.begin(), cdf.end(), target) - cdf.begin());
+    }
+  }
+  cudaStream_t s = h->model->stream;
+  DevBuf<long long> idx_dev;
+  DevBuf<double> out_dev;
+  THY_TRY(idx_dev.upload(idx, s));
+  THY_TRY(out_dev.reserve((size_t)n * h->d));
+  k_slq_gather_rows<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(n, h->d, idx_dev.ptr, h->ret_x.ptr, out_dev.ptr);
+  count_launch();
+  THY_CUDA_CHECK(cudaMemcpyAsync(out_samples, out_dev.ptr, (size_t)n * h->d * sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
   return THY_OK;
 }
 

@@ -11,8 +11,7 @@
 // once per CTA with the row pitch = 4 (mod 8) the fused evaluation kernel uses, so the forward pass Z = X A^T runs on
 // the fp64 tensor cores straight from the walker registers; priors, residuals and the Metropolis test are quad
 // reductions.  No walker state touches HBM between the spawn and the commit.
-#include "kernels.h"
-#include "philox.cuh"
+#include "slq_internal.h"
 #include "ptx.cuh"
 
 namespace thy {
@@ -28,12 +27,14 @@ struct WalkParams {
   int n, n_pad, d;
   int distribution;
   double log_const;
-  int c;                 // walkers this round
+  const int* c_dev;      // walkers this round = local retirees (device word written by the selection step)
   long long Pl;
   int M;
-  uint64_t seed, round;
+  uint64_t seed;
+  const long long* round_dev;   // round number (device word: the launch replays from a CUDA graph)
   int rank;
-  const int* sidx;       // live-pool indices in ascending log-likelihood order
+  const int* sidx;       // [c] retired slots (ascending)
+  const unsigned char* flags;   // [Pl] 1 = retired this round
   double* x;             // [Pl][d] live pool
   double* ll;            // [Pl]
   double* lpr;           // [Pl]
@@ -81,20 +82,21 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
   const double thr = p.scalars[1];
   const int ngrp = p.n_pad / 8;
   const int d = p.d;
+  const int c = *p.c_dev;
+  const uint64_t round = (uint64_t)*p.round_dev;
 
-  for (long long grp = (long long)blockIdx.x * WNW + warp; grp * 8 < p.c; grp += (long long)gridDim.x * WNW) {
+  for (long long grp = (long long)blockIdx.x * WNW + warp; grp * 8 < c; grp += (long long)gridDim.x * WNW) {
     const long long w = grp * 8 + g8;
-    const bool live = w < p.c;
+    const bool live = w < c;
     const uint64_t key = ((uint64_t)p.rank << 40) | (uint64_t)(live ? w : 0);
     // ---- spawn: a uniformly chosen survivor (same draw as k_slq_spawn) ----
-    int src = 0, slot = 0;
+    long long src = 0;
+    int slot = 0;
     if (live) {
-      const RngDraw u = rng_uniform2(p.seed, key, 0, RNG_SLQ_PICK, p.round);
-      long long pick = p.c + (long long)(u.u0 * (double)(p.Pl - p.c));
-      if (pick >= p.Pl) pick = p.Pl - 1;
-      src = p.sidx[pick];
+      if (q4 == 0) src = slq_pick_survivor(p.seed, key, round, p.Pl, p.flags);
       slot = p.sidx[w];
     }
+    src = __shfl_sync(0xffffffffu, src, lane & ~3);   // one lane of the quad draws, the quad shares the pick
     double xf[KS], xp[KS];
 #pragma unroll
     for (int kk = 0; kk < KS; ++kk) {
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
     int acc = 0;
 
     for (int step = 0; step < p.M; ++step) {
-      const uint64_t gstep = p.round * (uint64_t)p.M + (uint64_t)step;
+      const uint64_t gstep = round * (uint64_t)p.M + (uint64_t)step;
       // ---- propose + prior of the proposal ----
       double pacc = 0.0;
       bool inside = true;
@@ -187,12 +189,13 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
 }
 
 template <int NT>
-thy_status launch_walk_nt(const WalkParams& p, size_t smem, cudaStream_t s) {
+thy_status launch_walk_nt(const WalkParams& p, int c_max, size_t smem, cudaStream_t s) {
   THY_CUDA_CHECK(cudaFuncSetAttribute(k_slq_walk<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   THY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_slq_walk<NT>, WNW * 32, smem));
   if (per_sm < 1) per_sm = 1;
-  const long long groups = (p.c + 7) / 8;
+  // sized for the largest possible retire count; the kernel reads the actual one from device memory (grid-stride loop)
+  const long long groups = (c_max + 7) / 8;
   long long blocks = (groups + WNW - 1) / WNW;
   const long long cap = (long long)sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
@@ -221,10 +224,10 @@ bool slq_walk_supported(const thy_model_s* m) {
   return walk_smem_bytes(lk, nt) <= (size_t)200 * 1024;
 }
 
-thy_status launch_slq_walk(thy_model_s* m, int c, long long Pl, int M, uint64_t seed, uint64_t round, int rank,
-                           const int* sidx, double* x, double* ll, double* lpr, const double* sigma, const double* scalars,
-                           int* accepted, cudaStream_t s) {
-  if (c <= 0) return THY_OK;
+thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long long Pl, int M, uint64_t seed,
+                           const long long* round_dev, int rank, const int* sidx, const unsigned char* flags, double* x,
+                           double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s) {
+  if (c_max <= 0) return THY_OK;
   const LikDev& lk = m->lik_dev[0]->view;
   WalkParams p{};
   p.A = lk.A;
@@ -235,13 +238,14 @@ thy_status launch_slq_walk(thy_model_s* m, int c, long long Pl, int M, uint64_t 
   p.d = m->d;
   p.distribution = lk.distribution;
   p.log_const = lk.log_const;
-  p.c = c;
+  p.c_dev = c_dev;
   p.Pl = Pl;
   p.M = M;
   p.seed = seed;
-  p.round = round;
+  p.round_dev = round_dev;
   p.rank = rank;
   p.sidx = sidx;
+  p.flags = flags;
   p.x = x;
   p.ll = ll;
   p.lpr = lpr;
@@ -251,7 +255,7 @@ thy_status launch_slq_walk(thy_model_s* m, int c, long long Pl, int M, uint64_t 
   const int nt = fused_nt_for(lk.dl);
   const size_t smem = walk_smem_bytes(lk, nt);
   switch (nt) {
-#define THY_WALK_CASE(N) case N: return launch_walk_nt<N>(p, smem, s);
+#define THY_WALK_CASE(N) case N: return launch_walk_nt<N>(p, c_max, smem, s);
     THY_WALK_CASE(1) THY_WALK_CASE(2) THY_WALK_CASE(3) THY_WALK_CASE(4) THY_WALK_CASE(5) THY_WALK_CASE(7)
     THY_WALK_CASE(10) THY_WALK_CASE(13) THY_WALK_CASE(16)
 #undef THY_WALK_CASE

@@ -278,6 +278,13 @@ register("thy_slq_retired", C.c_int, [_vp, C.c_int64, _dp, _i64p])
 register("thy_slq_sample", C.c_int, [_vp, C.c_int, C.c_uint64, _dp])
 register("thy_slq_abscissa_results", C.c_int, [_vp, _dp, _dp])
 register("thy_slq_live_points", C.c_int, [_vp, _i64p, _dp, _dp])
+register("thy_slq_retired_log_x", C.c_int, [_vp, C.c_int, C.c_int64, _dp, _i64p])
+SLQ_INTEGRAND = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+register("thy_slq_integrate", C.c_int, [_vp, SLQ_INTEGRAND, C.c_void_p, C.c_double, _dp, _dp, _dp])
+register("thy_slq_set_trace", C.c_int, [_vp, C.c_int])
+register("thy_slq_phase_times", C.c_int, [_vp, _dp, _i64p])
+SLQ_PHASES = ("pool_spread", "all_gather_keys", "radix_select_flags", "retired_values", "walk_adapt", "wait_quadrature",
+              "round_control")
 
 
 @dataclass
@@ -392,21 +399,38 @@ class SlqIntegratedPosterior:
         check(self._lib.thy_slq_retired(self._h, n.value, _ptr(out), C.byref(n)))
         return out
 
-    def integrate(self, integrand: Callable[[np.ndarray], np.ndarray]) -> float:
-        """QuadratureIntegrator.getIntegrationStats (QuadratureIntegrator.scala:64-83) under the expected abscissa:
-        sum_i w_i integrand(L_i) with L_i = exp(l_i - max l).  ``integrand`` maps an array of scaled likelihoods."""
-        ll = self.retiredLogLikelihoods()
-        world = self.comm.world if self.comm is not None else 1
-        P, live = self.config.poolSize, int(self.stats.iterations)
-        K = max(1, min(self.config.sampleParallelism, (P // world) // 2))      # the engine's clamp (thy_slq_create)
-        j = np.where(np.arange(ll.size) < live, np.arange(ll.size) % K, np.arange(ll.size) - live)
-        lx = np.concatenate([[0.0], np.cumsum(-1.0 / (P - j))])[:-1]
-        X = np.exp(lx)
-        w = np.empty_like(X)
-        w[1:-1] = 0.5 * (X[:-2] - X[2:])
-        w[0] = 0.5 * (X[0] - X[1])
-        w[-1] = 0.5 * (X[-2] - X[-1])
-        return float(np.sum(w * integrand(np.exp(ll - ll.max()))))
+    def retiredLogX(self, abscissa: int) -> np.ndarray:
+        """ln X_i of one simulated abscissa for the retired points (QuadratureAbscissa.scala:33-73), replayed on the
+        device from the counter RNG."""
+        n = C.c_int64()
+        check(self._lib.thy_slq_retired_log_x(self._h, abscissa, 0, None, C.byref(n)))
+        out = np.empty(n.value)
+        check(self._lib.thy_slq_retired_log_x(self._h, abscissa, n.value, _ptr(out), C.byref(n)))
+        return out
+
+    def integrate(self, integrand: Callable[[float], float], logShift: Optional[float] = None, reference: bool = False) -> float:
+        """``integrate`` (SlqEngine.scala:460-466): mean over the simulated abscissas of sum_i w_ai integrand(exp(l_i - s))
+        through the C ABI's ``thy_slq_integrate`` (host callback, as the reference's integrand is a JVM closure).
+        ``logShift`` None = max l (fp64-safe); NaN = the reference's (max l + min l) / 2.  ``reference=True`` returns the
+        statistic the reference's ``getIntegrationStats`` literally computes, mean_a (I_a / Z_a - ln Z_a)."""
+        if logShift is None:
+            logShift = float(self.retiredLogLikelihoods().max())
+        cb = SLQ_INTEGRAND(lambda v, _u: float(integrand(v)))
+        stat, integ = C.c_double(), C.c_double()
+        check(self._lib.thy_slq_integrate(self._h, cb, None, float(logShift), C.byref(stat), C.byref(integ), None))
+        return stat.value if reference else integ.value
+
+    def setTrace(self, enable: bool) -> None:
+        check(self._lib.thy_slq_set_trace(self._h, 1 if enable else 0))
+
+    def phaseTimes(self) -> Dict[str, float]:
+        """Mean microseconds per traced round of each phase (``setTrace(True)`` first)."""
+        us = np.zeros(7)
+        n = C.c_int64()
+        check(self._lib.thy_slq_phase_times(self._h, _ptr(us), C.byref(n)))
+        out = {k: float(v) for k, v in zip(SLQ_PHASES, us)}
+        out["rounds"] = int(n.value)
+        return out
 
     def sample(self, numberOfSamples: int, rngSeed: int = 1) -> List[Dict[str, np.ndarray]]:
         out = np.empty((numberOfSamples, self.posterior.domainDimension))
