@@ -46,6 +46,11 @@ typedef struct thy_surface_s* thy_surface_t;
 const char* thy_version(void);
 /* Message of the last failing call on this thread (never NULL). */
 const char* thy_last_error(void);
+/* Devices (a JVM cannot call the CUDA runtime itself): number of usable GPUs; bind the CALLING THREAD to one.  Every
+ * handle lives on the device that was current when it was created / finalized and must be used from a thread bound to
+ * that device. */
+thy_status thy_device_count(int* out_count);
+thy_status thy_set_device(int device);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches claim). */
 uint64_t thy_kernel_launch_count(void);
 
@@ -123,7 +128,9 @@ typedef enum thy_option {
   THY_OPT_FD_INCREMENTAL = 1,
   /* Kernel selection for linear-Gaussian terms: 0 = auto, 1 = force generic tiled kernels,
    * 2 = force fused DMMA kernel (error if the shape is unsupported), 3 = force streaming (small-batch) kernel,
-   * 4 = force the wide DMMA GEMM pair (any width / link; not for uniform observations or FD Jacobians).      */
+   * 4 = force the wide DMMA GEMM pair (any width / link; not for uniform observations or FD Jacobians),
+   * 5 = as 2 but always the variant that streams A through a TMA ring (2 and auto switch to the variant that keeps A
+   * resident in shared memory when it fits and the batch covers the SMs; reported as "resident_dmma").        */
   THY_OPT_KERNEL_PATH = 2,
   /* When a posterior is one linear term over the whole parameter vector with per-coordinate priors, the fused DMMA
    * kernel can evaluate the priors in its output step (one launch per evaluation, no read-modify-write of the
@@ -149,6 +156,9 @@ thy_status thy_model_collapse(thy_model_t m, thy_model_t* out);
  * of the unnormalised posterior (the analytic evidence the SLQ tests compare against). */
 thy_status thy_model_gaussian_posterior(thy_model_t m, double* out_mean, double* out_covariance, double* out_precision,
                                         double* out_log_evidence, double* out_max_logpdf);
+/* Handle-local error text: message of the last failing call made on this model or on a sampler built on it, from any
+ * thread (thy_last_error is per thread).  Copies at most capacity - 1 characters. */
+thy_status thy_model_last_error(thy_model_t m, char* out, size_t capacity);
 /* domainDimension (Posterior.scala:37-38) */
 thy_status thy_model_dimension(thy_model_t m, int* out_dim);
 /* offset and width of a label inside the flat vector (ModelParameterContext.scala:42-80) */
@@ -162,6 +172,14 @@ thy_status thy_model_synchronize(thy_model_t m);
  * Posterior.logPdfAt / logPdfGradientAt (posterior/Posterior.scala:50-73), batched over B points.       */
 thy_status thy_logpdf_batch(thy_model_t m, int64_t B, const double* X, double* out_logp);
 thy_status thy_logpdf_grad_batch(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad);
+/* Pipelined host-buffer variant: returns as soon as the copies and kernels are queued (pinned host buffers make the
+ * copies asynchronous).  Two staging sets alternate, so call k+1's input copy and call k-1's output copy run under call
+ * k's kernels.  *out_ticket identifies the call; the outputs (and X) belong to the library until thy_model_wait returns
+ * for that ticket (ticket <= 0: wait for every outstanding call).  A ticket two or more calls old has always completed.
+ * out_grad may be NULL (value only). */
+thy_status thy_logpdf_grad_batch_async(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad,
+                                       int64_t* out_ticket);
+thy_status thy_model_wait(thy_model_t m, int64_t ticket);
 /* Device-pointer variants (zero-copy; out_grad may be NULL for value only). */
 thy_status thy_logpdf_grad_batch_dev(thy_model_t m, int64_t B, const double* X_dev, double* logp_dev, double* grad_dev);
 /* Posterior.samplePriors (Posterior.scala:64-65): B independent prior draws with the counter-based RNG. */
@@ -204,6 +222,17 @@ thy_status thy_hmc_stats(thy_hmc_t h, int64_t* out_jump_attempts, int64_t* out_j
                          double* out_hamiltonian_differential);
 /* Current positions [n_chains * d] and log-posteriors [n_chains] (checkpoint / warm start). */
 thy_status thy_hmc_get_state(thy_hmc_t h, double* out_x, double* out_logp);
+/* Checkpoint / resume (the reference carries its chain position in a TxnVar, HmcmcSampledPosterior.scala:36,55-56, and
+ * has no seedable RNG; here the state of a run is the positions plus the trajectory counter that keys every draw):
+ * set_state uploads positions [n_chains * d], re-evaluates log-posterior and gradient there and sets the counter, after
+ * which the chains continue exactly as the run that was checkpointed (same handle configuration and rng_seed). */
+thy_status thy_hmc_set_state(thy_hmc_t h, const double* x, uint64_t trajectory_counter);
+thy_status thy_hmc_get_trajectory_counter(thy_hmc_t h, uint64_t* out_counter);
+/* 1 (default): when the posterior is one fused-DMMA launch (single linear term + per-coordinate priors) every leapfrog
+ * step is ONE kernel -- the gradient kernel's output step applies the momentum kicks and the drift, and on the last step
+ * the Hamiltonian, the Metropolis test and the state update (HmcmcEngine.scala:55-172).  0: separate elementwise kernels
+ * around the gradient evaluation (always used for models outside that shape). */
+thy_status thy_hmc_set_fused_steps(thy_hmc_t h, int enable);
 
 /* ---- Leapfrog MCMC (gradient-free ensemble sampler) -----------------------------------------------
  * LeapfrogMcmcSampledPosterior.of(leapfrogMcmcConfig, distanceCalculation, posterior, setCb, updateCb, seed)
@@ -240,6 +269,11 @@ thy_status thy_lfm_get_pool(thy_lfm_t h, double* out_x, double* out_logp);
 typedef struct thy_comm_s* thy_comm_t;
 thy_status thy_comm_unique_id(unsigned char out_id[128]);
 thy_status thy_comm_create(int rank, int world, const unsigned char unique_id[128], thy_comm_t* out);
+/* Single-process mode (one JVM driving the whole box): communicators for n_devices GPUs of this process at once
+ * (ncclCommInitAll), out[i] = rank i on devices[i] (NULL: devices 0 .. n-1).  Use one host thread per GPU, each bound
+ * with thy_set_device(devices[i]) before it builds its model / sampler and for every later call on them: collectives of
+ * different ranks must be in flight concurrently, which one thread issuing them in turn cannot guarantee. */
+thy_status thy_comm_create_all(int n_devices, const int* devices, thy_comm_t* out);
 thy_status thy_comm_destroy(thy_comm_t c);
 thy_status thy_comm_rank(thy_comm_t c, int* out_rank, int* out_world);
 /* In-place sum of a device fp64 buffer over all ranks on the given stream (no-op for world == 1 / NULL comm). */
@@ -313,9 +347,11 @@ thy_status thy_slq_retired_log_x(thy_slq_t h, int abscissa, int64_t max_count, d
 typedef double (*thy_slq_integrand)(double scaled_likelihood, void* user);
 thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* user, double log_shift,
                              double* out_reference_statistic, double* out_integral, double* out_per_abscissa_integral);
-/* Phase trace: while enabled, rounds run as plain launches with CUDA events between the phases (pool spread, all-gather of
- * the ranks' keys, radix select + flags, retired values, walk + adapt, wait for the quadrature stream, round control);
- * thy_slq_phase_times returns the mean microseconds per round of each and the number of traced rounds. */
+/* Phase trace: while enabled, rounds run as plain launches with CUDA events between the phases.  out_us[0..4] are the
+ * consecutive phases of a round on the main stream (all-gather of the ranks' keys; radix select + flags + retired
+ * values; walk + adapt; wait for the quadrature stream; round control), mean microseconds per traced round; out_us[5] the
+ * pool-spread kernels, which run on a side stream beside phases 0-1; out_us[6] = 1 when untraced full rounds replay from
+ * a CUDA graph, else 0. */
 thy_status thy_slq_set_trace(thy_slq_t h, int enable);
 thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_rounds);
 /* Per-abscissa ln Z_a and H_a of the quadrature so far (QuadratureIntegrator.scala:29-62); [abscissaNumber] each. */

@@ -23,8 +23,9 @@ def _posteriors(prob):
     return post, ref
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_hmc_replay_matches_reference_algorithm(use_graph):
+def test_hmc_replay_matches_reference_algorithm(use_graph, fused):
     import torch
     d, n = 6, 80
     prob = linear_gaussian_problem(d, n, seed=42)
@@ -36,7 +37,8 @@ def test_hmc_replay_matches_reference_algorithm(use_graph):
     B, rng_seed, n_samples = 5, 1234567, 4
     mean, _ = o.analytic_gaussian_posterior(prob["pm"], prob["pvar"], prob["A"], prob["y"], prob["var"])
     seeds = mean[None, :] + 0.05 * np.random.default_rng(0).standard_normal((B, d))
-    hmc = t.HmcmcSampledPosterior(cfg, post, seed=seeds, numberOfChains=B, rngSeed=rng_seed, useGraph=use_graph)
+    hmc = t.HmcmcSampledPosterior(cfg, post, seed=seeds, numberOfChains=B, rngSeed=rng_seed, useGraph=use_graph,
+                                  fusedSteps=fused)   # fused: one launch per leapfrog step (kernels_fused_dmma.cu emit step)
     got = hmc.sampleChains(n_samples)
     att, acc, dh = hmc.stats()
     for b in range(B):
@@ -132,3 +134,78 @@ def test_hmc_graph_survives_workspace_growth_on_the_same_posterior():
         hmc.close()
         post.close()
     assert np.array_equal(states[0][0], states[1][0]) and np.array_equal(states[0][1], states[1][1])
+
+
+@pytest.mark.parametrize("d,n,B,L", [(10, 1000, 700, 5), (100, 104, 1500, 3), (100, 10_000, 256, 4), (37, 64, 130, 1)])
+def test_hmc_fused_leapfrog_step_agrees_with_the_separate_kernels(d, n, B, L):
+    """One launch per leapfrog step (kicks, drift, Hamiltonian, Metropolis test and state update inside the gradient
+    kernel's output step -- streaming and resident variants, stream-K combine included) against the round-1 path of
+    separate elementwise kernels: same draws, same accept decisions, states equal to rounding."""
+    prob = linear_gaussian_problem(d, n, seed=d + n)
+    eps = 0.3 * 0.1 * np.sqrt(d / max(n, d))
+    cfg = t.HmcmcConfig(stepsBetweenSamples=1, stepsInDynamicsSimulation=L, warmupStepCount=2, dynamicsSimulationStepSize=eps)
+    mean, cov = o.analytic_gaussian_posterior(prob["pm"], prob["pvar"], prob["A"], prob["y"], prob["var"])
+    seeds = mean[None, :] + 2.0 * np.sqrt(np.diag(cov))[None, :] * np.random.default_rng(2).standard_normal((B, d))
+    out = []
+    for fused in (True, False):
+        post, _ = _posteriors(prob)
+        hmc = t.HmcmcSampledPosterior(cfg, post, seed=seeds, numberOfChains=B, rngSeed=77, fusedSteps=fused)
+        hmc.burnIn()
+        hmc.runTrajectories(6)
+        x, lp = hmc.state()
+        att, acc, dh = hmc.stats()
+        out.append((x, lp, att, acc, dh, hmc.trajectoryCounter()))
+        hmc.close()
+        post.close()
+    (xa, la, ata, aca, dha, ta), (xb, lb, atb, acb, dhb, tb) = out
+    assert ta == tb == 3 + 6 and np.array_equal(ata, atb)
+    same = aca == acb                                   # a decision can only differ where |u - exp(-dH)| ~ 1e-15
+    assert same.mean() > 0.999
+    sd = np.sqrt(np.diag(cov))
+    assert np.max(np.abs(xa[same] - xb[same]) / sd[None, :]) < 1e-8
+    assert np.max(np.abs(la[same] - lb[same]) / np.maximum(1.0, np.abs(lb[same]))) < 1e-10
+    assert 0.3 < aca.sum() / ata.sum() <= 1.0
+
+
+def test_hmc_checkpoint_resume_continues_the_same_chains():
+    """thy_hmc_set_state + trajectory counter (checkpoint row): a new sampler given the positions and
+    the counter of a checkpoint continues bit for bit like the run that was checkpointed."""
+    d, n, B = 12, 300, 96
+    prob = linear_gaussian_problem(d, n, seed=6)
+    cfg = t.HmcmcConfig(stepsBetweenSamples=1, stepsInDynamicsSimulation=4, warmupStepCount=3, dynamicsSimulationStepSize=0.004)
+    post, _ = _posteriors(prob)
+    a = t.HmcmcSampledPosterior(cfg, post, numberOfChains=B, rngSeed=21, seed={"theta": prob["theta"]})
+    a.burnIn()
+    a.runTrajectories(5)
+    x_ck, _ = a.state()
+    t_ck = a.trajectoryCounter()
+    a.runTrajectories(7)
+    x_end, lp_end = a.state()
+    b = t.HmcmcSampledPosterior(cfg, post, numberOfChains=B, rngSeed=21, seed={"theta": prob["theta"]})
+    b.setState(x_ck, t_ck)
+    b.runTrajectories(7)
+    x_res, lp_res = b.state()
+    assert t_ck == 4 + 5 and b.trajectoryCounter() == t_ck + 7
+    assert np.array_equal(x_end, x_res) and np.array_equal(lp_end, lp_res)
+    a.close()
+    b.close()
+    post.close()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_hmc_zero_dynamics_steps_always_accepts_with_zero_energy_error(fused):
+    """stepsInDynamicsSimulation = 0: the reference's leapfrog fold is empty, the proposal is the current point with the
+    momentum untouched, dH == 0 and the jump is always accepted (HmcmcEngine.scala:55-80, :128)."""
+    prob = linear_gaussian_problem(5, 60, seed=8)
+    post, _ = _posteriors(prob)
+    cfg = t.HmcmcConfig(stepsBetweenSamples=0, stepsInDynamicsSimulation=0, warmupStepCount=0, dynamicsSimulationStepSize=0.01)
+    hmc = t.HmcmcSampledPosterior(cfg, post, numberOfChains=40, rngSeed=3, seed={"theta": prob["theta"]}, fusedSteps=fused)
+    hmc.burnIn()
+    x0, lp0 = hmc.state()
+    hmc.runTrajectories(3)
+    x1, lp1 = hmc.state()
+    att, acc, dh = hmc.stats()
+    assert np.array_equal(x0, x1) and np.array_equal(lp0, lp1)
+    assert np.all(att == 4) and np.all(acc == 4) and np.all(dh == 0.0)
+    hmc.close()
+    post.close()

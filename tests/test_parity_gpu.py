@@ -107,7 +107,8 @@ def test_linear_gaussian_random(path, d, n, B):
         assert rel_err_grad(g, want_g) < TOL
         lp_only = post.logPdfBatch(X)
         assert np.array_equal(lp_only, lp) or rel_err_logp(lp_only, want_lp) < TOL
-    assert post.lastKernelPath == ("generic" if path == capi.KERNEL_GENERIC else "fused_dmma")
+    # the fused path has two variants: A streamed through a TMA ring, or resident in shared memory when it fits
+    assert post.lastKernelPath in (("generic",) if path == capi.KERNEL_GENERIC else ("fused_dmma", "resident_dmma"))
 
 
 def test_literal_dense_reference_agrees_at_small_size():
@@ -284,7 +285,7 @@ def test_full_size_config2_properties():
                                    [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
     X = typical_set_points(prob, 4096, seed=4)
     lp, g = post.logPdfGradBatch(X)
-    assert post.lastKernelPath == "fused_dmma"
+    assert post.lastKernelPath in ("fused_dmma", "resident_dmma")
     want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"],
                                               prior_var=prob["pvar"])
     assert rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
@@ -297,6 +298,72 @@ def test_full_size_config2_properties():
     quad = -0.5 * np.einsum("bi,ij,bj->b", D, lam, D)
     assert np.max(np.abs((lp - lp0[0]) - quad)) < 1e-9 * np.max(np.abs(quad)) + 1e-7
     assert np.max(np.abs(g + D @ lam)) < 1e-9 * gscale                        # grad = -Lambda (x - mu)
+
+
+# ---- resident variant of the fused kernel: A held in shared memory for the CTA's lifetime ---------------------------
+RESIDENT_SHAPES = [(100, 100, 4096), (100, 100, 4099), (100, 104, 700), (10, 1000, 5000), (128, 128, 1200), (3, 250, 9000),
+                   (64, 8, 333), (1, 1, 3000)]
+
+
+@pytest.mark.parametrize("d,n,B", RESIDENT_SHAPES)
+@pytest.mark.parametrize("fuse", [0, 2])
+def test_resident_kernel_matches_oracle_and_the_streaming_variant(d, n, B, fuse):
+    """kernels_fused_dmma.cu k_resident_dmma (the collapsed-model / config-1 shape) against the oracle, with the priors
+    folded into the output step (fusePrior=2) and added to a prior pass (0); the variant that streams A through the TMA
+    ring (kernelPath 5) must agree to rounding on the same inputs."""
+    prob = linear_gaussian_problem(d, n, seed=d * 31 + n)
+    mk = lambda path: t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                              [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")],
+                                              kernelPath=path, fusePrior=fuse)
+    res, stm = mk(capi.KERNEL_FUSED_DMMA), mk(capi.KERNEL_FUSED_STREAMING)
+    rng = np.random.default_rng(B)
+    X = (typical_set_points(prob, B, seed=B) if n >= d else rng.standard_normal((B, d)))
+    want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X, prior_mean=prob["pm"], prior_var=prob["pvar"])
+    lp, g = res.logPdfGradBatch(X)
+    assert res.lastKernelPath == "resident_dmma"
+    assert rel_err_logp(lp, want_lp) < TOL and rel_err_grad(g, want_g) < TOL
+    lp2, g2 = res.logPdfGradBatch(X)
+    assert np.array_equal(lp, lp2) and np.array_equal(g, g2)                # deterministic
+    assert rel_err_logp(res.logPdfBatch(X), want_lp) < TOL                  # value-only instantiation
+    lps, gs = stm.logPdfGradBatch(X)
+    assert stm.lastKernelPath == "fused_dmma"
+    assert rel_err_logp(lps, want_lp) < TOL and rel_err_grad(gs, want_g) < TOL
+    res.close()
+    stm.close()
+
+
+def test_async_host_buffer_calls_deliver_the_synchronous_results():
+    """thy_logpdf_grad_batch_async / thy_model_wait: calls pipelined two deep over two staging sets, batches of changing
+    size (a staging set has to grow while the other is in flight), value-only calls; every delivery equals the blocking call."""
+    import torch
+    prob = linear_gaussian_problem(24, 900, seed=12)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
+                                   [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
+    sizes = [300, 300, 1200, 64, 5000, 5000, 7, 2048]
+    Xs = [torch.from_numpy(typical_set_points(prob, B, seed=i)).pin_memory() for i, B in enumerate(sizes)]
+    lps = [torch.empty(B, dtype=torch.float64).pin_memory() for B in sizes]
+    gs = [torch.empty(B, 24, dtype=torch.float64).pin_memory() for B in sizes]
+    tickets = []
+    for i, B in enumerate(sizes):
+        grad = None if i == 3 else gs[i].numpy()
+        tickets.append(post.logPdfGradBatchAsync(Xs[i].numpy(), lps[i].numpy(), grad))
+        if i >= 1:
+            post.wait(tickets[i - 1])
+            # blocking call on the same model, in between.  It cuts batches >= 2048 into [small, large, small] chunks, so
+            # its stream-K partial sums combine in a different order: equal to rounding, not bit for bit
+            want_lp, want_g = post.logPdfGradBatch(Xs[i - 1].numpy())
+            assert rel_err_logp(lps[i - 1].numpy(), want_lp) < 1e-13
+            if i - 1 != 3:
+                assert rel_err_grad(gs[i - 1].numpy(), want_g) < 1e-12
+    assert tickets == list(range(1, len(sizes) + 1))
+    post.wait()
+    want_lp, want_g = post.logPdfGradBatch(Xs[-1].numpy())
+    assert rel_err_logp(lps[-1].numpy(), want_lp) < 1e-13 and rel_err_grad(gs[-1].numpy(), want_g) < 1e-12
+    # the same call twice delivers the same bits
+    lp2, g2 = torch.empty(2048, dtype=torch.float64).pin_memory(), torch.empty(2048, 24, dtype=torch.float64).pin_memory()
+    post.wait(post.logPdfGradBatchAsync(Xs[-1].numpy(), lp2.numpy(), g2.numpy()))
+    assert np.array_equal(lp2.numpy(), lps[-1].numpy()) and np.array_equal(g2.numpy(), gs[-1].numpy())
+    post.close()
 
 
 # ---- small-batch streaming kernel (B <= 8): TMA-staged memory-bound pass -----------------------------------
@@ -337,7 +404,7 @@ def test_stream_kernel_is_the_small_batch_default_and_rejects_large_batches():
     auto.logPdfGradBatch(typical_set_points(prob, 4, seed=1))
     assert auto.lastKernelPath == "stream_dmma"
     auto.logPdfGradBatch(typical_set_points(prob, 40, seed=1))
-    assert auto.lastKernelPath == "fused_dmma"
+    assert auto.lastKernelPath in ("fused_dmma", "resident_dmma")
     forced = t.UnnormalisedPosterior(pri, lik, kernelPath=capi.KERNEL_STREAM)
     X = typical_set_points(prob, 27, seed=1)                   # 4 groups of <= 8 chains, one pass over A each
     lp, g = forced.logPdfGradBatch(X)

@@ -23,7 +23,7 @@ DIST_GAUSSIAN, DIST_CAUCHY, DIST_UNIFORM = 0, 1, 2
 LINK_IDENTITY, LINK_TANH, LINK_EXP, LINK_SQUARE, LINK_SOFTPLUS, LINK_SIGMOID = range(6)
 JAC_CONSTANT, JAC_ANALYTIC, JAC_FINITE_DIFFERENCE = 0, 1, 2
 OPT_CAUCHY_REFERENCE_SIGN, OPT_FD_INCREMENTAL, OPT_KERNEL_PATH, OPT_FUSE_PRIOR = 0, 1, 2, 3
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED_DMMA, KERNEL_STREAM, KERNEL_WIDE = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED_DMMA, KERNEL_STREAM, KERNEL_WIDE, KERNEL_FUSED_STREAMING = 0, 1, 2, 3, 4, 5
 
 
 class ThylacineError(RuntimeError):
@@ -59,6 +59,9 @@ SIGNATURES = {
     "thy_version": (C.c_char_p, []),
     "thy_last_error": (C.c_char_p, []),
     "thy_kernel_launch_count": (C.c_uint64, []),
+    "thy_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "thy_set_device": (C.c_int, [C.c_int]),
+    "thy_model_last_error": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "thy_model_create": (C.c_int, [C.POINTER(_vp)]),
     "thy_model_destroy": (C.c_int, [_vp]),
     "thy_model_add_gaussian_prior_ci": (C.c_int, [_vp, C.c_char_p, C.c_int, _dp, _dp]),
@@ -75,6 +78,8 @@ SIGNATURES = {
     "thy_logpdf_batch": (C.c_int, [_vp, C.c_int64, _dp, _dp]),
     "thy_logpdf_grad_batch": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "thy_logpdf_grad_batch_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
+    "thy_logpdf_grad_batch_async": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp, C.POINTER(C.c_int64)]),
+    "thy_model_wait": (C.c_int, [_vp, C.c_int64]),
     "thy_model_last_kernel_path": (C.c_char_p, [_vp]),
     "thy_model_enable_timing": (C.c_int, [_vp, C.c_int]),
     "thy_model_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -335,6 +335,23 @@ class UnnormalisedPosterior:
         check(self._lib.thy_logpdf_grad_batch(self._h, X.shape[0], _ptr(X), _ptr(out), _ptr(grad)))
         return out, grad
 
+    def logPdfGradBatchAsync(self, X: np.ndarray, out_logp: np.ndarray, out_grad: Optional[np.ndarray]) -> int:
+        """Pipelined host-buffer evaluation (``thy_logpdf_grad_batch_async``): queues copies and kernels and returns a
+        ticket; ``X`` / ``out_*`` (C-contiguous fp64, ideally pinned) belong to the library until ``wait(ticket)``."""
+        import ctypes as C
+        B = X.shape[0]
+        assert X.flags.c_contiguous and X.dtype == np.float64 and X.shape[1] == self.domainDimension
+        assert out_logp.flags.c_contiguous and out_logp.size >= B
+        assert out_grad is None or (out_grad.flags.c_contiguous and out_grad.size >= B * self.domainDimension)
+        ticket = C.c_int64()
+        check(self._lib.thy_logpdf_grad_batch_async(self._h, B, _ptr(X), _ptr(out_logp),
+                                                    _ptr(out_grad) if out_grad is not None else None, C.byref(ticket)))
+        return int(ticket.value)
+
+    def wait(self, ticket: int = 0) -> None:
+        """Block until the async call ``ticket`` (0: every outstanding call) has delivered its outputs."""
+        check(self._lib.thy_model_wait(self._h, ticket))
+
     # -- batched surface (device pointers: torch CUDA fp64 tensors or raw ints)
     def logPdfGradBatchDevice(self, B: int, x_ptr: int, logp_ptr: int, grad_ptr: Optional[int]) -> None:
         check(self._lib.thy_logpdf_grad_batch_dev(self._h, B, x_ptr, logp_ptr, grad_ptr))

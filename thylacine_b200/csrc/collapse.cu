@@ -109,6 +109,7 @@ using namespace thy;
 extern "C" {
 
 thy_status thy_model_collapse(thy_model_t m, thy_model_t* out) {
+  thy::ErrScope _err_scope(m);
   if (!out) return fail(THY_ERR_INVALID_ARGUMENT, "null out pointer");
   *out = nullptr;
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
@@ -185,6 +186,7 @@ thy_status thy_model_collapse(thy_model_t m, thy_model_t* out) {
 
 thy_status thy_model_gaussian_posterior(thy_model_t m, double* out_mean, double* out_covariance, double* out_precision,
                                         double* out_log_evidence, double* out_max_logpdf) {
+  thy::ErrScope _err_scope(m);
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   THY_TRY(require_device());
   const int d = m->d;

@@ -4,6 +4,7 @@
 #include "comm.h"
 #include <dlfcn.h>
 #include <cstring>
+#include <vector>
 
 namespace thy {
 
@@ -15,6 +16,7 @@ struct NcclApi {
   void* lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -34,6 +36,7 @@ NcclApi& api() {
   if (!a.lib) return a;
   a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
   a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+  a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
   a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
   a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
@@ -115,6 +118,53 @@ thy_status thy_comm_create(int rank, int world, const unsigned char unique_id[12
     c->nccl_comm = nc;
   }
   *out = c;
+  return THY_OK;
+}
+
+thy_status thy_comm_create_all(int n_devices, const int* devices, thy_comm_t* out) {
+  if (!out || n_devices < 1) return fail(THY_ERR_INVALID_ARGUMENT, "bad arguments");
+  THY_TRY(require_device());
+  int have = 0;
+  THY_CUDA_CHECK(cudaGetDeviceCount(&have));
+  std::vector<int> devs(n_devices);
+  for (int i = 0; i < n_devices; ++i) {
+    devs[i] = devices ? devices[i] : i;
+    if (devs[i] < 0 || devs[i] >= have) return fail(THY_ERR_INVALID_ARGUMENT, "device index out of range");
+  }
+  std::vector<ncclComm_t> comms(n_devices, nullptr);
+  if (n_devices > 1) {
+    if (!api().ok || !api().CommInitAll) return fail(THY_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    int cur = 0;
+    cudaGetDevice(&cur);
+    ncclResult_t r = api().CommInitAll(comms.data(), n_devices, devs.data());
+    cudaSetDevice(cur);
+    if (r != 0) return nccl_fail(r, "ncclCommInitAll");
+  }
+  for (int i = 0; i < n_devices; ++i) {
+    auto* c = new (std::nothrow) thy_comm_s();
+    if (!c) return fail(THY_ERR_INVALID_ARGUMENT, "allocation failed");
+    c->rank = i;
+    c->world = n_devices;
+    c->nccl_comm = comms[i];
+    out[i] = c;
+  }
+  return THY_OK;
+}
+
+thy_status thy_device_count(int* out_count) {
+  if (!out_count) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *out_count = n;
+  return THY_OK;
+}
+
+thy_status thy_set_device(int device) {
+  THY_TRY(require_device());
+  THY_CUDA_CHECK(cudaSetDevice(device));
   return THY_OK;
 }
 

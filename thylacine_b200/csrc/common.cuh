@@ -14,6 +14,13 @@ namespace thy {
 // ---- error plumbing (no C++ exception crosses the ABI) ---------------------------------------------
 void set_last_error(const std::string& msg);
 thy_status fail(thy_status code, const std::string& msg);
+// Handle-local error text: every API entry point that takes a model (or a sampler built on one) opens an ErrScope; while
+// it is open, fail() also records the message in that model, where thy_model_last_error finds it from any thread.
+struct ErrScope {
+  thy_model_s* prev;
+  explicit ErrScope(thy_model_s* m);
+  ~ErrScope();
+};
 
 #define THY_CUDA_CHECK(expr)                                                                    \
   do {                                                                                          \

@@ -13,6 +13,7 @@ static int select_path(thy_model_s* m, const LikDev& lk, int64_t B, bool want_gr
   const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&
                        lk.distribution != THY_DIST_UNIFORM);
   int path = m->opt_kernel_path;
+  if (path == 5) path = 2;   // 5 = fused DMMA, streaming variant only (launch_fused_dmma looks at the option itself)
   if (path == 2 && !(linear && fused_dmma_supported(lk, want_grad))) {
     *st = fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");
     return 0;
@@ -77,6 +78,24 @@ static bool single_kernel_eval(thy_model_s* m, int64_t B, bool want_grad) {
   if (m->opt_fuse_prior >= 2) return true;
   const double t_prior = 5e-6 + (double)B * m->d * 24.0 / 6e12;
   return 0.03 * fused_cost_model(own.view, B) < t_prior;
+}
+
+// A leapfrog step can be folded into the gradient kernel's output step when the whole posterior is ONE fused-DMMA launch:
+// a single linear term over the whole flat vector with per-coordinate priors (fused_prior_supported).
+bool hmc_step_fusable(thy_model_s* m, int64_t B) {
+  if (!m || !m->finalized || m->lik_dev.size() != 1) return false;
+  LikDevOwner& own = *m->lik_dev[0];
+  if (!fused_prior_supported(m, own)) return false;
+  thy_status st = THY_OK;
+  const int path = select_path(m, own.view, B, true, &st);
+  return st == THY_OK && path == 2;
+}
+
+// Gradient at X with the HMC step `hf` applied in the same launch (samplers always use the correct Cauchy sign).
+thy_status eval_batch_hmc(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad_scratch, const HmcFuse& hf) {
+  if (!hmc_step_fusable(m, B)) return fail(THY_ERR_STATE, "the fused HMC step does not cover this model");
+  m->last_path = "fused_dmma";
+  return launch_fused_dmma(m, *m->lik_dev[0], B, X, logp, grad_scratch, -1.0, m->stream, true, &hf);
 }
 
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign,
@@ -183,33 +202,104 @@ static thy_status eval_host(thy_model_t m, int64_t B, const double* X, double* o
   return THY_OK;
 }
 
+// Pipelined host-buffer evaluation.  Call i uses staging set i % 2:
+//   H2D stream:     wait until call i-2's kernels have finished with the set's X     -> copy X in
+//   model stream:   wait for that copy and for call i-2's D2H copy of the set's outputs -> kernels
+//   D2H stream:     wait for the kernels -> copy logp / grad out
+// Nothing blocks the host; thy_model_wait(ticket) does.  With pinned buffers call i+1's input copy and call i-1's
+// output copy run under call i's kernels (PCIe is full duplex), so back-to-back calls run at the device rate.
+static thy_status eval_host_async(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad,
+                                  int64_t* out_ticket) {
+  if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
+  THY_TRY(require_device());
+  if (B <= 0) return fail(THY_ERR_INVALID_ARGUMENT, "batch size must be positive");
+  if (!X || !out_logp) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  THY_TRY(ensure_copy_streams(m));
+  const int64_t ticket = m->async_next_ticket++;
+  auto& set = m->async_set[ticket & 1];
+  const size_t nx = (size_t)B * m->d;
+  cudaStream_t s = m->stream;
+  if (!set.h2d_done) {
+    THY_CUDA_CHECK(cudaEventCreateWithFlags(&set.h2d_done, cudaEventDisableTiming));
+    THY_CUDA_CHECK(cudaEventCreateWithFlags(&set.compute_done, cudaEventDisableTiming));
+    THY_CUDA_CHECK(cudaEventCreateWithFlags(&set.d2h_done, cudaEventDisableTiming));
+  }
+  if (set.X.count < nx || set.logp.count < (size_t)B || (out_grad && set.grad.count < nx)) {
+    // growing a staging buffer frees the old one: the set's previous call must have drained
+    if (set.ticket) THY_CUDA_CHECK(cudaEventSynchronize(set.d2h_done));
+    THY_TRY(set.X.reserve(nx));
+    THY_TRY(set.logp.reserve((size_t)B));
+    if (out_grad) THY_TRY(set.grad.reserve(nx));
+  }
+  if (set.ticket) THY_CUDA_CHECK(cudaStreamWaitEvent(m->h2d_stream, set.compute_done, 0));
+  else {   // first use: order behind whatever the model stream is doing
+    THY_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
+    THY_CUDA_CHECK(cudaStreamWaitEvent(m->h2d_stream, m->ev_start, 0));
+  }
+  THY_CUDA_CHECK(cudaMemcpyAsync(set.X.ptr, X, nx * sizeof(double), cudaMemcpyHostToDevice, m->h2d_stream));
+  THY_CUDA_CHECK(cudaEventRecord(set.h2d_done, m->h2d_stream));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(s, set.h2d_done, 0));
+  if (set.ticket) THY_CUDA_CHECK(cudaStreamWaitEvent(s, set.d2h_done, 0));
+  THY_TRY(eval_batch_dev(m, B, set.X.ptr, set.logp.ptr, out_grad ? set.grad.ptr : nullptr, false));
+  THY_CUDA_CHECK(cudaEventRecord(set.compute_done, s));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(m->d2h_stream, set.compute_done, 0));
+  THY_CUDA_CHECK(cudaMemcpyAsync(out_logp, set.logp.ptr, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, m->d2h_stream));
+  if (out_grad)
+    THY_CUDA_CHECK(cudaMemcpyAsync(out_grad, set.grad.ptr, nx * sizeof(double), cudaMemcpyDeviceToHost, m->d2h_stream));
+  THY_CUDA_CHECK(cudaEventRecord(set.d2h_done, m->d2h_stream));
+  set.ticket = ticket;
+  if (out_ticket) *out_ticket = ticket;
+  return THY_OK;
+}
+
 }  // namespace thy
 
 using namespace thy;
 
 extern "C" {
 
+thy_status thy_logpdf_grad_batch_async(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad,
+                                       int64_t* out_ticket) {
+  thy::ErrScope _err_scope(m);
+  return eval_host_async(m, B, X, out_logp, out_grad, out_ticket);
+}
+
+thy_status thy_model_wait(thy_model_t m, int64_t ticket) {
+  thy::ErrScope _err_scope(m);
+  if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
+  for (auto& set : m->async_set) {
+    if (!set.ticket || !set.d2h_done) continue;
+    if (ticket <= 0 || set.ticket <= ticket) THY_CUDA_CHECK(cudaEventSynchronize(set.d2h_done));
+  }
+  return THY_OK;
+}
+
 thy_status thy_logpdf_batch(thy_model_t m, int64_t B, const double* X, double* out_logp) {
+  thy::ErrScope _err_scope(m);
   return eval_host(m, B, X, out_logp, nullptr);
 }
 
 thy_status thy_logpdf_grad_batch(thy_model_t m, int64_t B, const double* X, double* out_logp, double* out_grad) {
+  thy::ErrScope _err_scope(m);
   if (!out_grad) return fail(THY_ERR_INVALID_ARGUMENT, "null gradient pointer");
   return eval_host(m, B, X, out_logp, out_grad);
 }
 
 thy_status thy_logpdf_grad_batch_dev(thy_model_t m, int64_t B, const double* X_dev, double* logp_dev, double* grad_dev) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(require_device());
   return eval_batch_dev(m, B, X_dev, logp_dev, grad_dev, false);
 }
 
 thy_status thy_model_enable_timing(thy_model_t m, int enable) {
+  thy::ErrScope _err_scope(m);
   if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
   m->timing = enable != 0;
   return THY_OK;
 }
 
 thy_status thy_model_kernel_time(thy_model_t m, double* out_total_ms, int64_t* out_launches) {
+  thy::ErrScope _err_scope(m);
   if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
   double total = 0.0;
   int64_t n = 0;

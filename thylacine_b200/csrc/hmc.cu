@@ -11,6 +11,7 @@
 // with the trajectory counter held in device memory so a whole trajectory can be replayed from a CUDA graph.
 #include "kernels.h"
 #include "philox.cuh"
+#include <utility>
 
 struct thy_hmc_s {
   thy_model_s* model = nullptr;
@@ -21,6 +22,8 @@ struct thy_hmc_s {
   bool has_seed_points = false;
   thy::DevBuf<double> seed_points;                // [B][d] when provided
   thy::DevBuf<double> x, p, g, xn, gn;            // [B][d]; g, gn hold grad logp (not negated)
+  thy::DevBuf<double> xn2;                        // second position buffer of the fused leapfrog step (ping-pong)
+  bool fused_steps = true;
   thy::DevBuf<double> lp, lpn, H0, dH;            // [B]
   thy::DevBuf<long long> attempts, acceptances, block_acc, emitted;  // [B]
   thy::DevBuf<unsigned long long> traj;           // [1] trajectory counter (device)
@@ -158,14 +161,45 @@ static thy_status hmc_trajectory_launch(thy_hmc_s* h) {
   cudaStream_t s = m->stream;
   const long long B = h->B;
   const int d = h->d;
-  const double eps = h->cfg.dynamicsSimulationStepSize;
   const int L = h->cfg.stepsInDynamicsSimulation;
+  // no dynamics (L == 0): the reference returns (input, rawP) unchanged, so dH == 0 and the proposal is always accepted
+  // (HmcmcEngine.scala:55-80 with an empty fold): no kick, no drift
+  const double eps = L > 0 ? h->cfg.dynamicsSimulationStepSize : 0.0;
   const unsigned wblocks = (unsigned)ceil_div(B, 8);
   k_hmc_begin<<<wblocks, 256, 0, s>>>(B, d, h->seed, h->traj.ptr, h->x.ptr, h->g.ptr, h->lp.ptr, h->p.ptr, h->xn.ptr,
                                       h->H0.ptr, eps);
   count_launch();
+  if (L > 0 && h->fused_steps && hmc_step_fusable(m, B)) {
+    // ONE launch per leapfrog step: kicks / drift / Metropolis test live in the gradient kernel's output step
+    THY_TRY(h->xn2.reserve((size_t)B * d));
+    double* cur = h->xn.ptr;
+    double* nxt = h->xn2.ptr;
+    for (int l = 0; l < L; ++l) {
+      HmcFuse hf;
+      hf.mode = (l + 1 < L) ? HMC_FUSE_MID : HMC_FUSE_LAST;
+      hf.eps = eps;
+      hf.p = h->p.ptr;
+      hf.x_next = nxt;
+      hf.x = h->x.ptr;
+      hf.g = h->g.ptr;
+      hf.lp = h->lp.ptr;
+      hf.H0 = h->H0.ptr;
+      hf.dH = h->dH.ptr;
+      hf.attempts = h->attempts.ptr;
+      hf.acceptances = h->acceptances.ptr;
+      hf.block_acc = h->block_acc.ptr;
+      hf.seed = h->seed;
+      hf.traj = h->traj.ptr;
+      THY_TRY(eval_batch_hmc(m, B, cur, h->lpn.ptr, h->gn.ptr, hf));
+      if (l + 1 < L) std::swap(cur, nxt);
+    }
+    k_hmc_advance<<<1, 1, 0, s>>>(h->traj.ptr);
+    count_launch();
+    THY_CUDA_CHECK(cudaGetLastError());
+    return THY_OK;
+  }
   if (L <= 0) {
-    // no dynamics: the proposal is the current point; evaluate it so lpn / gn are defined
+    // the proposal is the current point; evaluate it so lpn / gn are defined
     THY_TRY(eval_batch_dev(m, B, h->x.ptr, h->lpn.ptr, h->gn.ptr, true));
     THY_CUDA_CHECK(cudaMemcpyAsync(h->xn.ptr, h->x.ptr, (size_t)B * d * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
@@ -178,7 +212,7 @@ static thy_status hmc_trajectory_launch(thy_hmc_s* h) {
   }
   k_hmc_end<<<wblocks, 256, 0, s>>>(B, d, h->seed, h->traj.ptr, h->x.ptr, h->g.ptr, h->lp.ptr, h->p.ptr, h->xn.ptr, h->gn.ptr,
                                     h->lpn.ptr, h->H0.ptr, h->dH.ptr, h->attempts.ptr, h->acceptances.ptr, h->block_acc.ptr,
-                                    L > 0 ? eps : 0.0);
+                                    eps);
   k_hmc_advance<<<1, 1, 0, s>>>(h->traj.ptr);
   count_launch(2);
   THY_CUDA_CHECK(cudaGetLastError());
@@ -257,6 +291,7 @@ extern "C" {
 
 thy_status thy_hmc_create(thy_model_t m, const thy_hmcmc_config* cfg, int64_t n_chains, uint64_t rng_seed,
                           const double* seed_points, thy_hmc_t* out) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(require_device());
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (!cfg || !out) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
@@ -300,17 +335,56 @@ thy_status thy_hmc_create(thy_model_t m, const thy_hmcmc_config* cfg, int64_t n_
 }
 
 thy_status thy_hmc_destroy(thy_hmc_t h) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   delete h;
   return THY_OK;
 }
 
+thy_status thy_hmc_set_fused_steps(thy_hmc_t h, int enable) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  h->fused_steps = enable != 0;
+  if (h->graph) {   // the captured trajectory belongs to the other mode
+    cudaGraphExecDestroy(h->graph);
+    h->graph = nullptr;
+  }
+  return THY_OK;
+}
+
+thy_status thy_hmc_set_state(thy_hmc_t h, const double* x, uint64_t trajectory_counter) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
+  if (!h || !x) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  thy_model_s* m = h->model;
+  cudaStream_t s = m->stream;
+  const unsigned long long t = trajectory_counter;
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->x.ptr, x, (size_t)h->B * h->d * sizeof(double), cudaMemcpyHostToDevice, s));
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->traj.ptr, &t, sizeof(t), cudaMemcpyHostToDevice, s));
+  THY_TRY(eval_batch_dev(m, h->B, h->x.ptr, h->lp.ptr, h->g.ptr, true));
+  THY_CUDA_CHECK(cudaMemsetAsync(h->block_acc.ptr, 0, h->B * sizeof(long long), s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));   // x and t are host stack / caller memory
+  h->initialised = true;
+  return THY_OK;
+}
+
+thy_status thy_hmc_get_trajectory_counter(thy_hmc_t h, uint64_t* out_counter) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
+  if (!h || !out_counter) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  unsigned long long t = 0;
+  THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
+  THY_CUDA_CHECK(cudaMemcpy(&t, h->traj.ptr, sizeof(t), cudaMemcpyDeviceToHost));
+  *out_counter = t;
+  return THY_OK;
+}
+
 thy_status thy_hmc_set_use_graph(thy_hmc_t h, int enable) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   h->use_graph = enable != 0;
   return THY_OK;
 }
 
 thy_status thy_hmc_burn_in(thy_hmc_t h) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   THY_TRY(hmc_initialise(h));
   THY_TRY(hmc_block(h, h->cfg.warmupStepCount));
@@ -319,6 +393,7 @@ thy_status thy_hmc_burn_in(thy_hmc_t h) {
 }
 
 thy_status thy_hmc_run_trajectories(thy_hmc_t h, int n_trajectories) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->initialised) THY_TRY(hmc_initialise(h));
   for (int i = 0; i < n_trajectories; ++i) THY_TRY(hmc_trajectory(h));
@@ -364,14 +439,17 @@ static thy_status hmc_sample_impl(thy_hmc_t h, int n_per_chain, double* out_host
 }
 
 thy_status thy_hmc_sample(thy_hmc_t h, int n_per_chain, double* out_samples, int rerun_burn_in) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   return hmc_sample_impl(h, n_per_chain, out_samples, nullptr, rerun_burn_in);
 }
 
 thy_status thy_hmc_sample_dev(thy_hmc_t h, int n_per_chain, double* out_samples_dev, int rerun_burn_in) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   return hmc_sample_impl(h, n_per_chain, nullptr, out_samples_dev, rerun_burn_in);
 }
 
 thy_status thy_hmc_stats(thy_hmc_t h, int64_t* out_attempts, int64_t* out_acceptances, double* out_last_dH) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   cudaStream_t s = h->model->stream;
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -384,6 +462,7 @@ thy_status thy_hmc_stats(thy_hmc_t h, int64_t* out_attempts, int64_t* out_accept
 }
 
 thy_status thy_hmc_get_state(thy_hmc_t h, double* out_x, double* out_logp) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
   if (out_x) THY_CUDA_CHECK(cudaMemcpy(out_x, h->x.ptr, (size_t)h->B * h->d * sizeof(double), cudaMemcpyDeviceToHost));

@@ -12,6 +12,29 @@ thy_status launch_prior(const PriorDev& pr, int64_t B, const double* X, double* 
 thy_status launch_generic_likelihood(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp,
                                      double* grad, double cauchy_sign, cudaStream_t s);
 
+// One leapfrog step of B lock-step HMC chains folded into the output step of the gradient kernel
+// (HmcmcEngine.scala:55-83): the kernel that owns a chain's complete gradient row also applies the momentum kicks and the
+// drift (MID), or the last half kick, the Hamiltonian, the Metropolis test and the state update (LAST).  Positions are
+// ping-ponged: the kernel reads X and writes x_next (stream-K tiles are read by several CTAs, so X is never updated in place).
+enum HmcFuseMode : int { HMC_FUSE_NONE = 0, HMC_FUSE_MID = 1, HMC_FUSE_LAST = 2 };
+struct HmcFuse {
+  int mode = HMC_FUSE_NONE;
+  double eps = 0.0;
+  double* p = nullptr;            // [B][d] momenta (read-modify-write)
+  double* x_next = nullptr;       // MID: [B][d] positions after the drift
+  // LAST:
+  double* x = nullptr;            // [B][d] chain state, overwritten on acceptance
+  double* g = nullptr;            // [B][d] gradient at the chain state
+  double* lp = nullptr;           // [B]
+  const double* H0 = nullptr;     // [B]
+  double* dH = nullptr;           // [B]
+  long long* attempts = nullptr;
+  long long* acceptances = nullptr;
+  long long* block_acc = nullptr;
+  uint64_t seed = 0;
+  const unsigned long long* traj = nullptr;   // device trajectory counter (keys the acceptance draw)
+};
+
 // kernels_fused_dmma.cu -- linear forward model + Gaussian/Cauchy observations, fused forward/residual/adjoint
 int fused_nt_for(int dl);  // 0 when the width is not covered by the fused kernel
 bool fused_dmma_supported(const LikDev& lik, bool want_grad);
@@ -19,8 +42,10 @@ double fused_cost_model(const LikDev& lik, int64_t B);    // seconds, for auto-s
 // fuse_prior: the kernel also evaluates the per-coordinate priors and WRITES logp / grad (single term over the whole
 // flat vector, no Cauchy / full-covariance prior blocks: fused_prior_supported)
 bool fused_prior_supported(const thy_model_s* m, const LikDevOwner& lik);
+// The launcher picks the resident variant (A held in shared memory for the CTA's lifetime) when resident_dmma_supported.
+bool resident_dmma_supported(const LikDev& lik, int64_t B);
 thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
-                             double cauchy_sign, cudaStream_t s, bool fuse_prior = false);
+                             double cauchy_sign, cudaStream_t s, bool fuse_prior = false, const HmcFuse* hmc = nullptr);
 
 // kernels_stream.cu -- small-batch memory-bound pass (A streamed once per batch)
 bool stream_supported(const LikDev& lik, int64_t B);

@@ -22,6 +22,7 @@
 //     the last warp to deliver its segment (atomic ticket per (tile, warp)): deterministic, and ONE launch per term.
 // Z = A X (n x B, 328 MB at the 100-d / 10k-obs / 4096-chain config) is never materialised.
 #include "kernels.h"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace thy {
@@ -58,6 +59,10 @@ struct FusedParams {
   const double* pr_p0;
   const double* pr_p1;
   double pr_log_const;
+  // resident variant: 8-row groups actually holding observations (rows beyond n are zero padding and are skipped)
+  int nrg;
+  // HMC step folded into the output step (needs fuse_prior): see HmcFuse in kernels.h
+  HmcFuse hmc;
 };
 
 template <int NT>
@@ -89,9 +94,11 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
   const double sc = WANT_GRAD ? apply_scale(p.distribution, qsum, p.n, p.cauchy_sign) : 0.0;
   // fused priors (the term reads the whole flat vector in order: column j IS coordinate j)
   const double* xrow = p.X + chain * p.d;
+  const int mode = WANT_GRAD ? p.hmc.mode : 0;
   double* grow = WANT_GRAD ? p.grad + chain * p.d : nullptr;
-  double acc = 0.0;
+  double acc = 0.0, kin = 0.0;
   bool inside = true;
+  const double he = -p.hmc.eps / 2;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
 #pragma unroll
@@ -109,7 +116,23 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
         } else if (kind == PK_UNIFORM) {
           inside = inside && (xv >= p.pr_p0[j]) && (xv < p.pr_p1[j]);
         }
-        if (WANT_GRAD) grow[j] = gj + sc * ga[WANT_GRAD ? t : 0][h];
+        if (WANT_GRAD) {
+          gj = gj + sc * ga[WANT_GRAD ? t : 0][h];
+          if (mode == HMC_FUSE_NONE) {
+            grow[j] = gj;
+          } else if (mode == HMC_FUSE_MID) {
+            // second half kick of this leapfrog step, first half kick and drift of the next (HmcmcEngine.scala:55-80;
+            // the reference works with -grad logp: p += (-g)(-eps/2), twice, then x += eps p)
+            const double kick = __dmul_rn(-gj, he);
+            double pv = __dadd_rn(p.hmc.p[chain * p.d + j], kick);
+            pv = __dadd_rn(pv, kick);
+            p.hmc.p[chain * p.d + j] = pv;
+            p.hmc.x_next[chain * p.d + j] = __dadd_rn(xv, __dmul_rn(pv, p.hmc.eps));
+          } else {
+            const double pv = __dadd_rn(p.hmc.p[chain * p.d + j], __dmul_rn(-gj, he));   // last half kick
+            kin += pv * pv;
+          }
+        }
       }
     }
   }
@@ -117,7 +140,48 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
   const unsigned ballot = __ballot_sync(0xffffffffu, inside);
   const int lane = threadIdx.x & 31;
   const bool inside_all = ((ballot >> (lane & ~3)) & 0xFu) == 0xFu;
-  if (live && q4 == 0) p.logp[chain] = (inside_all ? (-0.5 * acc + p.pr_log_const) : -INFINITY) + lik;
+  const double lp_new = (inside_all ? (-0.5 * acc + p.pr_log_const) : -INFINITY) + lik;
+  if (mode != HMC_FUSE_LAST) {
+    if (live && q4 == 0) p.logp[chain] = lp_new;
+    return;
+  }
+  if (WANT_GRAD) {
+    // trajectory end (HmcmcEngine.scala:82-172): H1 = p.p/2 - logp, accept iff dH < 0 || U < exp(-dH); state update
+    kin = quad_sum(kin);
+    bool accept = false;
+    double dH = 0.0;
+    if (live) {
+      const double H1 = kin / 2.0 + (-lp_new);
+      dH = H1 - p.hmc.H0[chain];
+      const RngDraw u = rng_uniform2(p.hmc.seed, (uint64_t)chain, 0, RNG_HMC_ACCEPT, *p.hmc.traj);
+      accept = (dH < 0) || (u.u0 < exp(-dH));   // NaN dH -> reject, as in the reference
+    }
+    if (accept) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 8 * t + 2 * q4 + h;
+          if (j < p.dl) {
+            // the gradient is recomputed (same operations, same value) rather than kept in 2 NT more registers
+            const double xv = xrow[j];
+            const double gpr = (p.pr_kind[j] == PK_GAUSS_DIAG) ? (p.pr_p0[j] - xv) * p.pr_p1[j] : 0.0;
+            p.hmc.x[chain * p.d + j] = xv;
+            p.hmc.g[chain * p.d + j] = gpr + sc * ga[WANT_GRAD ? t : 0][h];
+          }
+        }
+      }
+    }
+    if (live && q4 == 0) {
+      if (accept) {
+        p.hmc.lp[chain] = lp_new;
+        p.hmc.acceptances[chain] += 1;
+        p.hmc.block_acc[chain] += 1;
+      }
+      p.hmc.attempts[chain] += 1;
+      p.hmc.dH[chain] = dH;
+    }
+  }
 }
 
 // Stream-K combine.  The last warp to deliver its segment of a (tile, warp) row group sums all segments, always in CTA
@@ -358,6 +422,165 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedPara
   if (cur_tile >= 0) flush(cur_tile, seg_begin, u1);
 }
 
+
+// ---- resident variant: the whole coefficient matrix stays in shared memory for the CTA's lifetime -------------------------
+// For models whose A fits one SM's shared memory (a collapsed posterior: d x d; BASELINE config 1: 1000 x 10) streaming A
+// through a ring per (tile, row block) unit is the wrong shape: every unit pays a barrier round trip, the X-fragment
+// prologue and the output step for a few row blocks of work, and 4096 chains are only 64 tiles for 148 SMs.  Here each
+// CTA loads A once (TMA bulk copies on one mbarrier, overlapped with the first X-fragment loads), and its warps then work
+// through 8-chain groups independently -- no CTA-wide synchronisation after the load, so one warp's prologue / output step
+// overlaps its neighbours' DMMAs.  Work is distributed by WARP (group = 8 chains), and the CTA width is chosen by the
+// launcher so that small batches still cover all SMs (4096 chains = 512 groups -> 128 CTAs of 4 warps).  Row groups
+// beyond the last observation are skipped (n' = 100 pads to 128 rows: 13 groups instead of 16).  Same fragment scheme,
+// same arithmetic per row as the streaming kernel above.
+template <int NT, int JGN, bool WANT_GRAD>
+__device__ __forceinline__ void resident_rows(const double* __restrict__ As, const double2* __restrict__ Ys, int off1,
+                                              int off2_s0, int off2_s1, int pi_s0, int pi_s1, const double (&xf)[2 * NT],
+                                              double (&ga)[WANT_GRAD ? NT : 1][2], double& ssq) {
+  using C = Cfg<NT>;
+  double z[JGN][2];
+#pragma unroll
+  for (int j = 0; j < JGN; ++j) z[j][0] = z[j][1] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < C::KS; ++kk) {
+#pragma unroll
+    for (int j = 0; j < JGN; ++j) ptx::dmma884(z[j][0], z[j][1], xf[kk], As[off1 + j * 8 * C::LDS + 4 * kk]);
+  }
+#pragma unroll
+  for (int j = 0; j < JGN; ++j) {
+    const double2 y0 = Ys[j * 8 + pi_s0];
+    const double2 y1 = Ys[j * 8 + pi_s1];
+    const double r0 = y0.x - z[j][0];
+    const double r1 = y1.x - z[j][1];
+    const double w0 = r0 * y0.y;
+    const double w1 = r1 * y1.y;
+    ssq = fma(r0, w0, ssq);
+    ssq = fma(r1, w1, ssq);
+    z[j][0] = w0;
+    z[j][1] = w1;
+  }
+  if (WANT_GRAD) {
+#pragma unroll
+    for (int j = 0; j < JGN; ++j) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ptx::dmma884(ga[t][0], ga[t][1], z[j][0], As[off2_s0 + j * 8 * C::LDS + 8 * t]);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ptx::dmma884(ga[t][0], ga[t][1], z[j][1], As[off2_s1 + j * 8 * C::LDS + 8 * t]);
+    }
+  }
+}
+
+template <int NT, bool WANT_GRAD, bool FUSE_PRIOR>
+__global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams p) {
+  using C = Cfg<NT>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int rows = p.nrg * 8;
+  double* As = reinterpret_cast<double*>(smem);
+  double2* Ys = reinterpret_cast<double2*>(smem + (size_t)rows * C::LDS * 8);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)rows * (C::LDS * 8 + 16));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)rows * (C::LDS * 8 + 16));
+    for (int r0 = 0; r0 < rows; r0 += 64) {   // <= 64 rows (67 KB) per bulk copy
+      const int nr = (rows - r0 < 64) ? (rows - r0) : 64;
+      ptx::bulk_g2s(As + (size_t)r0 * C::LDS, p.A + (size_t)r0 * C::LDS, (uint32_t)nr * C::LDS * 8, bar);
+    }
+    ptx::bulk_g2s(Ys, p.yiv, (uint32_t)rows * 16, bar);
+  }
+
+  const int g8 = lane >> 2, q4 = lane & 3;
+  const int pi_g = (g8 < 4) ? g8 : (g8 ^ 1);
+  const int pi_s0 = (q4 < 2) ? (2 * q4) : (2 * q4 + 1);
+  const int pi_s1 = (q4 < 2) ? (2 * q4 + 1) : (2 * q4);
+  const int off1 = pi_g * C::LDS + q4;
+  const int off2_s0 = pi_s0 * C::LDS + g8;
+  const int off2_s1 = pi_s1 * C::LDS + g8;
+  const long long ngroups = (p.B + 7) / 8;
+  bool loaded = false;
+  for (long long grp = (long long)blockIdx.x * nwarps + warp; grp < ngroups; grp += (long long)gridDim.x * nwarps) {
+    const long long chain = grp * 8 + g8;
+    double xf[C::KS];
+#pragma unroll
+    for (int kk = 0; kk < C::KS; ++kk) {
+      const int k = 4 * kk + q4;
+      xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + p.col[k]] : 0.0;
+    }
+    if (!loaded) {
+      ptx::mbar_wait(bar, 0);
+      loaded = true;
+    }
+    double ga[WANT_GRAD ? NT : 1][2];
+    if (WANT_GRAD) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ga[t][0] = ga[t][1] = 0.0;
+    }
+    double ssq = 0.0;
+    int rg = 0;
+    for (; rg + JG <= p.nrg; rg += JG)
+      resident_rows<NT, JG, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+    const int rem = p.nrg - rg;
+    if (rem == 3) resident_rows<NT, 3, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+    else if (rem == 2) resident_rows<NT, 2, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+    else if (rem == 1) resident_rows<NT, 1, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+    const double qsum = quad_sum(ssq);
+    if (FUSE_PRIOR) {
+      emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qsum, ga);
+    } else if (chain < p.B) {
+      if (q4 == 0) p.logp[chain] += apply_logp(p.distribution, qsum, p.n, p.log_const);
+      if (WANT_GRAD) {
+        const double sc = apply_scale(p.distribution, qsum, p.n, p.cauchy_sign);
+        double* grow = p.grad + chain * p.d;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int j = 8 * t + 2 * q4;
+          if (j < p.dl) grow[p.col[j]] += sc * ga[WANT_GRAD ? t : 0][0];
+          if (j + 1 < p.dl) grow[p.col[j + 1]] += sc * ga[WANT_GRAD ? t : 0][1];
+        }
+      }
+    }
+  }
+  // a CTA must not retire while its bulk copies are in flight: warp 0 always sees them land
+  if (warp == 0 && !loaded) ptx::mbar_wait(bar, 0);
+}
+
+static size_t resident_smem_bytes(int nrg, int lds) { return (size_t)nrg * 8 * ((size_t)lds * 8 + 16) + 16; }
+
+template <int NT>
+thy_status launch_resident_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_t s) {
+  const size_t smem = resident_smem_bytes(p.nrg, Cfg<NT>::LDS);
+  const long long ngroups = (p.B + 7) / 8;
+  const int sms = sm_count();
+  // CTA width: enough warps to hold the work, few enough that small batches still reach every SM
+  int warps = (int)((ngroups + sms - 1) / sms);
+  warps = warps < 1 ? 1 : (warps > NW ? NW : warps);
+  if (warps == 3) warps = 4;
+  if (warps > 4 && warps < NW) warps = NW;
+  long long grid = (ngroups + warps - 1) / warps;
+  if (grid > sms) grid = sms;
+  KernelTimer timer(m, s);
+  auto launch = [&](auto kernel) -> thy_status {
+    THY_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)grid, warps * 32, smem, s>>>(p);
+    return THY_OK;
+  };
+  if (p.fuse_prior) {
+    THY_TRY(want_grad ? launch(k_resident_dmma<NT, true, true>) : launch(k_resident_dmma<NT, false, true>));
+  } else {
+    THY_TRY(want_grad ? launch(k_resident_dmma<NT, true, false>) : launch(k_resident_dmma<NT, false, false>));
+  }
+  timer.stop();
+  count_launch();
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
+}
+
 template <int NT>
 thy_status launch_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_t s) {
   using C = Cfg<NT>;
@@ -421,10 +644,23 @@ bool fused_prior_supported(const thy_model_s* m, const LikDevOwner& lik) {
          !lik.col_host.empty() && lik.col_host[0] == 0;
 }
 
+// Resident variant: A (rows that hold observations) + (y, 1/var) fit one CTA's shared memory.  Preferred whenever the
+// batch gives every SM at least a few groups, or the model is so short that streaming it makes no sense.
+bool resident_dmma_supported(const LikDev& lik, int64_t B) {
+  if (!fused_dmma_supported(lik, true)) return false;
+  const int nrg = (lik.n + 7) / 8;
+  if (resident_smem_bytes(nrg, lik.lds) > (size_t)200 * 1024) return false;
+  return lik.n_pad <= 256 || (B + 7) / 8 >= sm_count() / 2;
+}
+
 thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, const double* X, double* logp, double* grad,
-                             double cauchy_sign, cudaStream_t s, bool fuse_prior) {
+                             double cauchy_sign, cudaStream_t s, bool fuse_prior, const HmcFuse* hmc) {
   const LikDev& lk = lik.view;
   FusedParams p{};
+  if (hmc) {
+    if (!fuse_prior || !grad) return fail(THY_ERR_STATE, "the fused HMC step needs the fused-prior output step and a gradient");
+    p.hmc = *hmc;
+  }
   if (fuse_prior) {
     if (!fused_prior_supported(m, lik)) return fail(THY_ERR_STATE, "fused priors requested for an unsupported model");
     p.fuse_prior = 1;
@@ -449,7 +685,23 @@ thy_status launch_fused_dmma(thy_model_s* m, const LikDevOwner& lik, int64_t B, 
   p.distribution = lk.distribution;
   p.log_const = lk.log_const;
   p.cauchy_sign = cauchy_sign;
+  p.nrg = (lk.n + 7) / 8;
   const bool wg = grad != nullptr;
+  if (m->opt_kernel_path != 5 && resident_dmma_supported(lk, B)) {   // 5: the streaming variant is asked for explicitly
+    m->last_path = "resident_dmma";
+    switch (fused_nt_for(lk.dl)) {
+      case 1: return launch_resident_nt<1>(m, p, wg, s);
+      case 2: return launch_resident_nt<2>(m, p, wg, s);
+      case 3: return launch_resident_nt<3>(m, p, wg, s);
+      case 4: return launch_resident_nt<4>(m, p, wg, s);
+      case 5: return launch_resident_nt<5>(m, p, wg, s);
+      case 7: return launch_resident_nt<7>(m, p, wg, s);
+      case 10: return launch_resident_nt<10>(m, p, wg, s);
+      case 13: return launch_resident_nt<13>(m, p, wg, s);
+      case 16: return launch_resident_nt<16>(m, p, wg, s);
+      default: return fail(THY_ERR_UNSUPPORTED, "resident DMMA: unsupported width");
+    }
+  }
   switch (fused_nt_for(lk.dl)) {
     case 1: return launch_nt<1>(m, p, wg, s);
     case 2: return launch_nt<2>(m, p, wg, s);

@@ -247,6 +247,7 @@ extern "C" {
 
 thy_status thy_lfm_create(thy_model_t m, const thy_leapfrog_mcmc_config* cfg, int distance, uint64_t rng_seed,
                           const double* seed_point, thy_lfm_t* out) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(require_device());
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (!cfg || !out) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
@@ -287,17 +288,20 @@ thy_status thy_lfm_create(thy_model_t m, const thy_leapfrog_mcmc_config* cfg, in
 }
 
 thy_status thy_lfm_destroy(thy_lfm_t h) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   delete h;
   return THY_OK;
 }
 
 thy_status thy_lfm_run_sweeps(thy_lfm_t h, int n_sweeps) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   for (int i = 0; i < n_sweeps; ++i) THY_TRY(lfm_sweep(h));
   return THY_OK;
 }
 
 thy_status thy_lfm_sample(thy_lfm_t h, int n, double* out_samples) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (n <= 0 || !out_samples) return fail(THY_ERR_INVALID_ARGUMENT, "bad arguments");
   cudaStream_t s = h->model->stream;
@@ -319,6 +323,7 @@ thy_status thy_lfm_sample(thy_lfm_t h, int n, double* out_samples) {
 }
 
 thy_status thy_lfm_stats(thy_lfm_t h, uint64_t* out_proposals, uint64_t* out_acceptances) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   unsigned long long c[2];
   THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
@@ -329,6 +334,7 @@ thy_status thy_lfm_stats(thy_lfm_t h, uint64_t* out_proposals, uint64_t* out_acc
 }
 
 thy_status thy_lfm_get_pool(thy_lfm_t h, double* out_x, double* out_logp) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
   if (out_x) THY_CUDA_CHECK(cudaMemcpy(out_x, h->x.ptr, (size_t)h->P * h->d * sizeof(double), cudaMemcpyDeviceToHost));

@@ -10,15 +10,24 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 
 namespace thy {
 
 static thread_local std::string t_last_error = "";
 std::atomic<uint64_t> g_kernel_launches{0};
 
+static thread_local thy_model_s* t_scope_model = nullptr;
+ErrScope::ErrScope(thy_model_s* m) : prev(t_scope_model) { t_scope_model = m; }
+ErrScope::~ErrScope() { t_scope_model = prev; }
+
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 thy_status fail(thy_status code, const std::string& msg) {
   t_last_error = msg;
+  if (t_scope_model) {
+    std::lock_guard<std::mutex> lock(t_scope_model->err_mutex);
+    t_scope_model->last_error = msg;
+  }
   return code;
 }
 
@@ -195,6 +204,12 @@ extern "C" {
 
 const char* thy_version(void) { return "thylacine_b200 0.1 (sm_100a)"; }
 const char* thy_last_error(void) { return thy::t_last_error.c_str(); }
+thy_status thy_model_last_error(thy_model_t m, char* out, size_t capacity) {
+  if (!m || !out || capacity == 0) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  std::lock_guard<std::mutex> lock(m->err_mutex);
+  std::snprintf(out, capacity, "%s", m->last_error.c_str());
+  return THY_OK;
+}
 uint64_t thy_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 thy_status thy_model_create(thy_model_t* out) {
@@ -205,6 +220,14 @@ thy_status thy_model_create(thy_model_t* out) {
 }
 
 thy_status thy_model_destroy(thy_model_t m) {
+  if (m) {
+    for (auto& set : m->async_set) {
+      if (set.d2h_done) cudaEventSynchronize(set.d2h_done);   // an outstanding async call still owns the staging buffers
+      if (set.h2d_done) cudaEventDestroy(set.h2d_done);
+      if (set.compute_done) cudaEventDestroy(set.compute_done);
+      if (set.d2h_done) cudaEventDestroy(set.d2h_done);
+    }
+  }
   if (m && m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m && m->h2d_stream) {
     cudaStreamDestroy(m->h2d_stream);
@@ -221,6 +244,7 @@ thy_status thy_model_destroy(thy_model_t m) {
 
 thy_status thy_model_add_gaussian_prior_ci(thy_model_t m, const char* label, int dim, const double* values,
                                            const double* ci) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   THY_TRY(check_label(m, label, dim));
   if (!values || !ci) return fail(THY_ERR_INVALID_ARGUMENT, "null array");
@@ -236,6 +260,7 @@ thy_status thy_model_add_gaussian_prior_ci(thy_model_t m, const char* label, int
 
 thy_status thy_model_add_gaussian_prior_cov(thy_model_t m, const char* label, int dim, const double* values,
                                             const double* cov) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   THY_TRY(check_label(m, label, dim));
   if (!values || !cov) return fail(THY_ERR_INVALID_ARGUMENT, "null array");
@@ -259,6 +284,7 @@ thy_status thy_model_add_gaussian_prior_cov(thy_model_t m, const char* label, in
 
 thy_status thy_model_add_uniform_prior(thy_model_t m, const char* label, int dim, const double* max_bounds,
                                        const double* min_bounds) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   THY_TRY(check_label(m, label, dim));
   if (!max_bounds || !min_bounds) return fail(THY_ERR_INVALID_ARGUMENT, "null array");
@@ -276,6 +302,7 @@ thy_status thy_model_add_uniform_prior(thy_model_t m, const char* label, int dim
 }
 
 thy_status thy_model_add_cauchy_prior(thy_model_t m, const char* label, int dim, const double* values, const double* ci) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   THY_TRY(check_label(m, label, dim));
   if (!values || !ci) return fail(THY_ERR_INVALID_ARGUMENT, "null array");
@@ -290,6 +317,7 @@ thy_status thy_model_add_cauchy_prior(thy_model_t m, const char* label, int dim,
 }
 
 thy_status thy_model_add_likelihood(thy_model_t m, const thy_likelihood_desc* d) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   if (!d) return fail(THY_ERR_INVALID_ARGUMENT, "null descriptor");
   if (d->n <= 0 || d->nblocks <= 0) return fail(THY_ERR_INVALID_ARGUMENT, "n and nblocks must be positive");
@@ -343,6 +371,7 @@ thy_status thy_model_add_likelihood(thy_model_t m, const thy_likelihood_desc* d)
 }
 
 thy_status thy_model_set_option(thy_model_t m, int option, int value) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   switch (option) {
     case THY_OPT_CAUCHY_REFERENCE_SIGN: m->opt_cauchy_ref_sign = value ? 1 : 0; return THY_OK;
@@ -351,7 +380,7 @@ thy_status thy_model_set_option(thy_model_t m, int option, int value) {
       m->opt_fd_incremental = value;
       return THY_OK;
     case THY_OPT_KERNEL_PATH:
-      if (value < 0 || value > 4) return fail(THY_ERR_INVALID_ARGUMENT, "kernel path must be 0..4");
+      if (value < 0 || value > 5) return fail(THY_ERR_INVALID_ARGUMENT, "kernel path must be 0..5");
       m->opt_kernel_path = value;
       return THY_OK;
     case THY_OPT_FUSE_PRIOR:
@@ -367,6 +396,7 @@ thy_status thy_model_set_option(thy_model_t m, int option, int value) {
 // poisoned and every later call on it reports THY_ERR_STATE (the caller destroys it and builds a new model).
 static thy_status finalize_impl(thy_model_t m);
 thy_status thy_model_finalize(thy_model_t m) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, false));
   const thy_status st = finalize_impl(m);
   if (st != THY_OK && st != THY_ERR_NO_DEVICE) m->poisoned = true;
@@ -505,6 +535,7 @@ static thy_status finalize_impl(thy_model_t m) {
 }
 
 thy_status thy_model_dimension(thy_model_t m, int* out_dim) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, true));
   if (!out_dim) return fail(THY_ERR_INVALID_ARGUMENT, "null out pointer");
   *out_dim = m->d;
@@ -512,6 +543,7 @@ thy_status thy_model_dimension(thy_model_t m, int* out_dim) {
 }
 
 thy_status thy_model_label_layout(thy_model_t m, const char* label, int* out_offset, int* out_dim) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, true));
   if (!label) return fail(THY_ERR_INVALID_ARGUMENT, "null label");
   auto it = m->layout.find(label);
@@ -522,12 +554,14 @@ thy_status thy_model_label_layout(thy_model_t m, const char* label, int* out_off
 }
 
 thy_status thy_model_set_stream(thy_model_t m, void* cuda_stream) {
+  thy::ErrScope _err_scope(m);
   if (!m) return fail(THY_ERR_INVALID_ARGUMENT, "null model handle");
   m->stream = cuda_stream ? (cudaStream_t)cuda_stream : (m->own_stream ? m->own_stream : (cudaStream_t)0);
   return THY_OK;
 }
 
 thy_status thy_model_synchronize(thy_model_t m) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(check_model(m, true));
   THY_CUDA_CHECK(cudaStreamSynchronize(m->stream));
   return THY_OK;

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <map>
 #include <memory>
+#include <mutex>
 
 namespace thy {
 
@@ -96,6 +97,8 @@ struct Workspace {  // grow-only scratch owned by the model, reused across evalu
 struct thy_model_s {
   std::vector<thy::PriorHost> priors;
   std::vector<thy::LikelihoodHost> liks;
+  std::string last_error;   // message of the last failing call made on this handle (or a sampler built on it)
+  std::mutex err_mutex;
   bool finalized = false;
   bool poisoned = false;   // a finalize failed half-way: the handle only accepts thy_model_destroy
   int d = 0;
@@ -122,6 +125,14 @@ struct thy_model_s {
   // host-pointer API: copy streams + events so the H2D / D2H copies of one chunk overlap the kernels of the next
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d[8] = {}, ev_done[8] = {}, ev_start = nullptr;
+  // asynchronous host-buffer calls (thy_logpdf_grad_batch_async): two staging sets so that call k+1's H2D copy overlaps
+  // call k's kernels and call k-1's D2H copy; per-set events order the reuse without blocking the host
+  struct AsyncSet {
+    thy::DevBuf<double> X, logp, grad;
+    cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    int64_t ticket = 0;   // last call that used this set
+  } async_set[2];
+  int64_t async_next_ticket = 1;
   // optional CUDA-event timing of the dominant kernel (bench.py's roofline leg)
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -155,6 +166,9 @@ struct KernelTimer {
 // eval.cu
 thy_status eval_batch_dev(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad, bool cauchy_correct_sign = false,
                           bool likelihoods_only = false);
+struct HmcFuse;
+bool hmc_step_fusable(thy_model_s* m, int64_t B);
+thy_status eval_batch_hmc(thy_model_s* m, int64_t B, const double* X, double* logp, double* grad_scratch, const HmcFuse& hf);
 thy_status launch_likelihood(thy_model_s* m, LikDevOwner& owner, int64_t B, const double* X, double* logp, double* grad,
                              double csign, cudaStream_t s, bool fuse_prior = false);
 // model.cu

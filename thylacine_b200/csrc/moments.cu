@@ -78,6 +78,7 @@ using namespace thy;
 extern "C" {
 
 thy_status thy_moments_reset_dev(thy_model_t m, double* acc_dev) {
+  thy::ErrScope _err_scope(m);
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (!acc_dev) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
   THY_TRY(require_device());
@@ -87,6 +88,7 @@ thy_status thy_moments_reset_dev(thy_model_t m, double* acc_dev) {
 }
 
 thy_status thy_moments_accumulate_dev(thy_model_t m, int64_t n, const double* X_dev, double* acc_dev) {
+  thy::ErrScope _err_scope(m);
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (n < 0) return fail(THY_ERR_INVALID_ARGUMENT, "negative count");
   if (n == 0) return THY_OK;
@@ -110,6 +112,7 @@ thy_status thy_moments_accumulate_dev(thy_model_t m, int64_t n, const double* X_
 
 thy_status thy_moments_finish(thy_model_t m, thy_comm_t comm, double* acc_dev, double* out_count, double* out_mean,
                               double* out_cov) {
+  thy::ErrScope _err_scope(m);
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (!acc_dev) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
   THY_TRY(require_device());

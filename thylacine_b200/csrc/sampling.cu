@@ -60,11 +60,13 @@ using namespace thy;
 extern "C" {
 
 thy_status thy_sample_priors_dev(thy_model_t m, int64_t B, uint64_t rng_seed, double* X_dev) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(require_device());
   return sample_priors_dev(m, B, rng_seed, X_dev);
 }
 
 thy_status thy_sample_priors(thy_model_t m, int64_t B, uint64_t rng_seed, double* out_X) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(require_device());
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (B <= 0) return THY_OK;

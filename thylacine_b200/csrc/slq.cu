@@ -45,7 +45,7 @@ struct thy_slq_s {
   thy::DevBuf<int> sidx, count_dev;
   thy::DevBuf<double> vals_raw, vals_sorted;             // retired values of the round, unordered / ascending
   thy::DevBuf<int> pair_in, pair_out;                    // slot ids beside the keys (drain / keepRetiredPoints)
-  thy::DevBuf<unsigned char> cub_tmp;
+  thy::DevBuf<unsigned char> cub_tmp, cub_tmp2;          // sort scratch: quadrature stream / main stream (pairs)
   thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers of the per-step path
   thy::DevBuf<int> slot, accepted;
   thy::DevBuf<double> sigma, sig_part;                   // per-dimension spread of the live pool
@@ -61,7 +61,8 @@ struct thy_slq_s {
   long long ret_capacity = 0;
   bool fused_walk = false;             // slq_walk.cu covers this model: one kernel per round instead of 5 per walk step
   cudaStream_t side = nullptr;         // quadrature update runs beside the walk
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;        // pool spread runs beside the all-gather and the selection
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_sigma = nullptr;
   cudaEvent_t ev_round[3] = {};        // completion of round r is ev_round[r % 3]
   double* host_ao = nullptr;           // pinned [A][2] copy of abs_out
   int* host_c = nullptr;               // pinned copy of the local retire count (per-step path)
@@ -73,7 +74,7 @@ struct thy_slq_s {
   bool sort_sized = false;             // cub scratch sized (first round runs outside the graph)
   // phase trace (thy_slq_set_trace / THY_SLQ_TRACE=1): CUDA-event times of the round's phases, plain launches
   bool trace = false;
-  cudaEvent_t tev[8] = {};
+  cudaEvent_t tev[8] = {};             // [0..5] phase boundaries on the main stream, [6], [7] around the pool spread
   double tsum[7] = {0, 0, 0, 0, 0, 0, 0};
   long long tcount = 0;
   bool finished = false;
@@ -81,8 +82,11 @@ struct thy_slq_s {
   ~thy_slq_s() {
     if (graph) cudaGraphExecDestroy(graph);
     if (side) cudaStreamDestroy(side);
+    if (side2) cudaStreamDestroy(side2);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_fork2) cudaEventDestroy(ev_fork2);
+    if (ev_sigma) cudaEventDestroy(ev_sigma);
     for (auto& e : ev_round) if (e) cudaEventDestroy(e);
     for (auto& e : tev) if (e) cudaEventDestroy(e);
     if (host_ao) cudaFreeHost(host_ao);
@@ -93,8 +97,10 @@ struct thy_slq_s {
 
 namespace thy {
 
-static const char* const kPhaseNames[7] = {"pool spread", "all-gather of keys", "radix select + flags", "retired values",
-                                           "walk + adapt", "wait for quadrature", "round control"};
+// [0..4]: consecutive phases of the main stream (they add up to the round); [5]: the pool-spread kernels, which run on
+// their own stream beside phases 0-1; [6]: unused
+static const char* const kPhaseNames[7] = {"all-gather of keys", "radix select + flags + retired values", "walk + adapt",
+                                           "wait for quadrature", "round control", "pool spread (side stream)", "-"};
 
 __global__ void k_iota(int n, int* v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,12 +358,12 @@ static thy_status slq_sort_pairs(thy_slq_s* h, const double* kin, double* kout, 
                                  cudaStream_t s) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, 64, s);
-  if (bytes > h->cub_tmp.count) {
+  if (bytes > h->cub_tmp2.count) {
     THY_CUDA_CHECK(cudaStreamSynchronize(s));
     THY_CUDA_CHECK(cudaStreamSynchronize(h->side));
-    THY_TRY(h->cub_tmp.reserve(bytes));
+    THY_TRY(h->cub_tmp2.reserve(bytes));
   }
-  THY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.ptr, bytes, kin, kout, vin, vout, n, 0, 64, s));
+  THY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->cub_tmp2.ptr, bytes, kin, kout, vin, vout, n, 0, 64, s));
   count_launch(3);
   return THY_OK;
 }
@@ -380,25 +386,27 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   const SelectBuffers sb = sel_buffers(h);
   auto mark = [&](int i) { if (tracing) cudaEventRecord(h->tev[i], s); };
   mark(0);
-  // ---- proposal spread of the live pool (strided subsample) ----
+  // ---- proposal spread of the live pool (strided subsample), beside the all-gather and the selection ----
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_fork2, s));
+  THY_CUDA_CHECK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
+  if (tracing) cudaEventRecord(h->tev[6], h->side2);
   const long long nrows = std::min<long long>(h->Pl, 65536), row_stride = h->Pl / nrows;
   const int nslab = (int)std::min<long long>(296, nrows);
-  k_slq_sigma_part<<<nslab, 256, 0, s>>>(nrows, row_stride, d, h->x.ptr, h->sig_part.ptr, nslab);
-  k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(nrows, d, h->sig_part.ptr, nslab, h->sigma.ptr);
+  k_slq_sigma_part<<<nslab, 256, 0, h->side2>>>(nrows, row_stride, d, h->x.ptr, h->sig_part.ptr, nslab);
+  k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, h->side2>>>(nrows, d, h->sig_part.ptr, nslab, h->sigma.ptr);
   count_launch(2);
-  mark(1);
+  if (tracing) cudaEventRecord(h->tev[7], h->side2);
+  THY_CUDA_CHECK(cudaEventRecord(h->ev_sigma, h->side2));
   // ---- every rank sees every log-likelihood: ONE collective per round ----
   const double* keys = h->ll.ptr;
   if (h->world > 1) {
     THY_TRY(comm_all_gather_f64(h->comm, h->ll.ptr, h->keys_all.ptr, (size_t)h->Pl, s));
     keys = h->keys_all.ptr;
   }
+  mark(1);
+  // ---- threshold = K-th smallest; this rank's retirees; the retired values (before the walk overwrites their slots) ----
+  THY_TRY(slq_select_launch(sb, keys, h->Pl, h->world, h->rank, Kr, h->vals_raw.ptr, s));
   mark(2);
-  // ---- threshold = K-th smallest; this rank's retirees ----
-  THY_TRY(slq_select_launch(sb, keys, h->Pl, h->world, h->rank, Kr, s));
-  mark(3);
-  THY_TRY(slq_gather_retired_values(sb, keys, h->P, Kr, h->vals_raw.ptr, s));   // before the walk overwrites retired slots
-  mark(4);
   // ---- quadrature update beside the walk ----
   THY_CUDA_CHECK(cudaEventRecord(h->ev_fork, s));
   THY_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
@@ -419,6 +427,7 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
     count_launch(2);
   }
   // ---- replacement: constrained walks from survivors ----
+  THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sigma, 0));
   if (h->fused_walk) {
     THY_TRY(launch_slq_walk(m, Kr, h->count_dev.ptr, h->Pl, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->sidx.ptr, h->flags.ptr,
                             h->x.ptr, h->ll.ptr, h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s));
@@ -452,12 +461,12 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability,
                                  h->count_dev.ptr, h->M, h->accepted.ptr);
   count_launch();
-  mark(5);
+  mark(3);
   THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
-  mark(6);
+  mark(4);
   k_slq_advance<<<1, 1, 0, s>>>(h->ctl.ptr, Kr);
   count_launch();
-  mark(7);
+  mark(5);
   THY_CUDA_CHECK(cudaGetLastError());
   return THY_OK;
 }
@@ -504,11 +513,13 @@ static thy_status slq_round(thy_slq_s* h, int Kr) {
   }
   THY_CUDA_CHECK(cudaEventRecord(h->ev_round[h->rounds % 3], s));
   if (h->trace) {
-    THY_CUDA_CHECK(cudaEventSynchronize(h->tev[7]));
-    for (int i = 0; i < 7; ++i) {
+    THY_CUDA_CHECK(cudaEventSynchronize(h->tev[5]));
+    for (int i = 0; i < 5; ++i) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]) == cudaSuccess) h->tsum[i] += ms;
     }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->tev[6], h->tev[7]) == cudaSuccess) h->tsum[5] += ms;
     h->tcount += 1;
   }
   h->iterations += Kr;
@@ -578,6 +589,7 @@ extern "C" {
 
 thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng_seed, const double* seeds, int n_seeds,
                           thy_comm_t comm, thy_slq_t* out) {
+  thy::ErrScope _err_scope(m);
   THY_TRY(require_device());
   if (!m || !m->finalized) return fail(THY_ERR_STATE, "model is not finalized");
   if (!cfg || !out) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
@@ -617,7 +629,7 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   auto chk = [&](thy_status s2) { if (st == THY_OK) st = s2; };
   chk(h->x.reserve((size_t)Pl * d)); chk(h->ll.reserve(Pl)); chk(h->lpr.reserve(Pl));
   if (world > 1) chk(h->keys_all.reserve((size_t)h->P));
-  chk(h->sel_state.reserve(1)); chk(h->sel_hist.reserve(2048)); chk(h->sel_ticket.reserve(1)); chk(h->sel_cursor.reserve(1));
+  chk(h->sel_state.reserve(1)); chk(h->sel_hist.reserve(6 * 2048)); chk(h->sel_ticket.reserve(1)); chk(h->sel_cursor.reserve(1));
   chk(h->sel_cnt.reserve((size_t)spr * world)); chk(h->flags.reserve(Pl)); chk(h->sidx.reserve(K)); chk(h->count_dev.reserve(1));
   chk(h->vals_raw.reserve((size_t)KP)); chk(h->vals_sorted.reserve((size_t)KP));
   chk(h->pair_in.reserve((size_t)std::max<long long>(K, Pl))); chk(h->pair_out.reserve((size_t)std::max<long long>(K, Pl)));
@@ -637,6 +649,9 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   cudaStream_t s = m->stream;
   if (st == THY_OK) {
     bool ok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_sigma, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost(&h->host_ao, (size_t)h->A * 2 * sizeof(double)) == cudaSuccess &&
@@ -664,7 +679,7 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     chk(slq_eval(h, Pl, h->x.ptr, h->ll.ptr, h->lpr.ptr));
     std::vector<double> sc = {0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     bool ok = cudaMemsetAsync(h->accepted.ptr, 0, (size_t)K * sizeof(int), s) == cudaSuccess &&
-              cudaMemsetAsync(h->sel_hist.ptr, 0, 2048 * sizeof(unsigned int), s) == cudaSuccess &&
+              cudaMemsetAsync(h->sel_hist.ptr, 0, 6 * 2048 * sizeof(unsigned int), s) == cudaSuccess &&
               cudaMemsetAsync(h->sel_ticket.ptr, 0, sizeof(unsigned int), s) == cudaSuccess &&
               cudaMemsetAsync(h->sel_cursor.ptr, 0, sizeof(unsigned int), s) == cudaSuccess &&
               cudaMemsetAsync(h->sel_state.ptr, 0, sizeof(SelectState), s) == cudaSuccess &&
@@ -689,15 +704,17 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
 }
 
 thy_status thy_slq_destroy(thy_slq_t h) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (h && h->trace && h->tcount > 0 && std::getenv("THY_SLQ_TRACE")) {
     std::fprintf(stderr, "[thy slq trace] rank %d: %lld rounds; us/round:", h->rank, h->tcount);
-    for (int i = 0; i < 7; ++i) std::fprintf(stderr, " %s %.1f%s", kPhaseNames[i], 1e3 * h->tsum[i] / h->tcount, i < 6 ? "," : "\n");
+    for (int i = 0; i < 6; ++i) std::fprintf(stderr, " %s %.1f%s", kPhaseNames[i], 1e3 * h->tsum[i] / h->tcount, i < 5 ? "," : "\n");
   }
   delete h;
   return THY_OK;
 }
 
 thy_status thy_slq_set_trace(thy_slq_t h, int enable) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (enable && !h->tev[0])
     for (auto& e : h->tev)
@@ -707,14 +724,17 @@ thy_status thy_slq_set_trace(thy_slq_t h, int enable) {
 }
 
 thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_rounds) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   for (int i = 0; i < 7; ++i)
     if (out_us) out_us[i] = h->tcount > 0 ? 1e3 * h->tsum[i] / h->tcount : 0.0;
+  if (out_us) out_us[6] = h->graph ? 1.0 : 0.0;   // 1 when untraced full rounds replay from a CUDA graph
   if (out_rounds) *out_rounds = h->tcount;
   return THY_OK;
 }
 
 thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (h->finished) return fail(THY_ERR_STATE, "the simulation has already been drained");
   bool conv = false;
@@ -724,6 +744,7 @@ thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged) {
 }
 
 thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (h->finished) {
     if (out_stats) *out_stats = h->stats;
@@ -787,6 +808,7 @@ thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
 
 /* Retired log-likelihoods in retirement order (live phase followed by the drained pool). */
 thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, int64_t* out_count) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   const long long n = std::min<long long>(max_count, h->iterations);
   if (out_loglik && n > 0) {
@@ -800,6 +822,7 @@ thy_status thy_slq_retired(thy_slq_t h, int64_t max_count, double* out_loglik, i
 /* ln X_i of one simulated abscissa for the retired points, in retirement order (QuadratureAbscissa.scala:33-73): the
  * prior-mass simulation is replayed on the device from the counter RNG, so nothing had to be stored during the run. */
 thy_status thy_slq_retired_log_x(thy_slq_t h, int abscissa, int64_t max_count, double* out_log_x, int64_t* out_count) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (abscissa < 0 || abscissa >= h->A) return fail(THY_ERR_INVALID_ARGUMENT, "abscissa index out of range");
   const long long n = std::min<long long>(max_count, h->iterations);
@@ -810,6 +833,7 @@ thy_status thy_slq_retired_log_x(thy_slq_t h, int abscissa, int64_t max_count, d
 
 /* The rank's live points and their log-likelihoods (the reference's `samples` map, SlqEngine.scala:120-143). */
 thy_status thy_slq_live_points(thy_slq_t h, int64_t* out_count, double* out_x, double* out_loglik) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (out_count) *out_count = h->Pl;
   THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
@@ -820,6 +844,7 @@ thy_status thy_slq_live_points(thy_slq_t h, int64_t* out_count, double* out_x, d
 
 /* Per-abscissa results of the quadrature so far: ln Z_a and H_a (QuadratureIntegrator.scala:29-62). */
 thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, double* out_neg_entropy) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   std::vector<double> ao((size_t)h->A * 2);
   THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
@@ -840,6 +865,7 @@ thy_status thy_slq_abscissa_results(thy_slq_t h, double* out_log_evidence, doubl
  * so callers may pass e.g. max l).  The integrand is a host callback, as the reference's is a JVM closure. */
 thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* user, double log_shift,
                              double* out_reference_statistic, double* out_integral, double* out_per_abscissa_integral) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (!integrand) return fail(THY_ERR_INVALID_ARGUMENT, "null integrand");
   if (!h->finished) return fail(THY_ERR_STATE, "run the simulation first (rebuildSampleSimulation)");
@@ -881,6 +907,7 @@ thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* use
  * 1/2 (L_i + L_next)(X_i - X_next) (the innermost point: L X).  The staircases are built on the host from the exported
  * ln X; the chosen points are gathered on the device and copied back in ONE transfer.  Requires keepRetiredPoints. */
 thy_status thy_slq_sample(thy_slq_t h, int n, uint64_t rng_seed, double* out_samples) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->finished) return fail(THY_ERR_STATE, "run the simulation first (rebuildSampleSimulation)");
   if (!h->cfg.keepRetiredPoints || h->world != 1) return fail(THY_ERR_UNSUPPORTED, "retired points were not kept");

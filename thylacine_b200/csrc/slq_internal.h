@@ -18,9 +18,9 @@ struct SelectState {
 
 struct SelectBuffers {
   SelectState* state;
-  unsigned int* hist;     // [2048], zero between passes
-  unsigned int* ticket;   // [1], zero between passes
-  unsigned int* cursor;   // [1] append cursor of the retired-value gather
+  unsigned int* hist;     // [6][2048] one histogram per radix pass, zero between rounds
+  unsigned int* ticket;   // [1] grid-barrier counter (monotonic)
+  unsigned int* cursor;   // [1] append cursor of the retired values, zero between rounds
   int2* cnt;              // [world * slices_per_rank] (below, equal) per slice
   unsigned char* flags;   // [Pl] 1 = retired this round
   int* sidx;              // [K] retired local slots, ascending
@@ -55,9 +55,7 @@ __device__ __forceinline__ long long slq_pick_survivor(uint64_t seed, uint64_t k
 
 int slq_select_slices(long long Pl);
 thy_status slq_select_launch(const SelectBuffers& b, const double* keys, long long Pl, int world, int rank, int K,
-                             cudaStream_t s);
-thy_status slq_gather_retired_values(const SelectBuffers& b, const double* keys, long long n, int Kr, double* out,
-                                     cudaStream_t s);
+                             double* vals, cudaStream_t s);
 
 // ---- prior-mass simulation and quadrature (slq_evidence.cu) ----
 constexpr int EV_STATE = 12;   // doubles of carried state per abscissa

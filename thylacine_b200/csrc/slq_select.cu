@@ -1,30 +1,37 @@
-// SLQ threshold step on the device: exact selection of the K lowest live points WITHOUT sorting the pool.
+// SLQ threshold step on the device: exact selection of the K lowest live points WITHOUT sorting the pool, as ONE
+// persistent kernel.
 // Reference step being replaced: SlqEngine.scala:139-143 (`keys.min` of the live pool, one point per iteration) inside
 // the sampling loop :120-169; here the K = sampleParallelism lowest are retired per round (DESIGN.md "SLQ").
 //
 // Round 1 sorted every rank's whole local pool with cub::DeviceRadixSort (8 passes over keys AND indices, ~11 kernels,
 // 116-150 us at 125 000 keys) although only the K-th smallest VALUE and the SET of points below it are needed on the
-// critical path.  This file replaces that with a hand-written MSD radix select:
-//   k_sel_pass   6 passes over the keys (11, 11, 11, 11, 11, 9 bits of the order-preserving 64-bit image of the fp64
-//                log-likelihood).  Every CTA histograms the keys that still match the decided prefix in shared memory,
-//                merges into a global histogram, and the LAST CTA to finish (atomic ticket) scans it, extends the
-//                prefix by one digit and re-arms the histogram.  After the last pass the prefix IS the K-th smallest
-//                key, bit for bit, and the remainder says how many of the keys equal to it still have to go.
-//   k_sel_count  per 2048-key slice: how many keys are below the threshold / equal to it.
-//   k_sel_flag   local slices only: retire flags and an index-ordered (deterministic) compaction of the retired slots.
+// critical path.  k_slq_select is a hand-written MSD radix select, one CTA per SM, grid barriers between its phases
+// (cooperative launch: all CTAs are co-resident):
+//   passes 0-5   11, 11, 11, 11, 11, 9 bits of the order-preserving 64-bit image of the fp64 log-likelihood.  Every CTA
+//                histograms the keys that still match the decided prefix in shared memory (whole warps hit one bin in
+//                the early passes, so equal digits are aggregated with match.any first), merges into a global
+//                histogram, and after the barrier every CTA scans it and extends the prefix by one digit.  After the
+//                last pass the prefix IS the K-th smallest key, bit for bit, and the remainder says how many of the keys
+//                equal to it still have to go.
+//   count        per 2048-key slice of the GLOBAL key array: keys below / equal to the threshold; the retired VALUES
+//                (all keys below the threshold + the ties that go) are appended, unordered, to the quadrature's input
+//                (they are sorted on the quadrature stream, off the critical path).
+//   flag         local slices only: retire flags and an index-ordered (deterministic) compaction of the retired slots.
 //                Ties at the threshold are taken in global index order (rank-major), so exactly K points retire
 //                world-wide even when walkers that never moved left exact duplicates in the pool (the reference nudges
 //                duplicates by one ulp instead, SlqEngine.scala:107-118).
 // Across GPUs the keys of all ranks are all-gathered first (8 MB at 10^6 live points); every rank then runs the same
 // selection on the same array and derives its own retirees -- no second collective, identical thresholds everywhere.
-// The keys are read from L2 after the first pass (8 MB << 126 MB), so a pass costs a few microseconds.
+// The keys are read from L2 after the first pass (8 MB << 126 MB); all comparisons are made on the integer images, so
+// the count / flag phases agree bit for bit with the radix passes (-0.0 vs +0.0, NaNs).
 #include "slq_internal.h"
 
 namespace thy {
 
 namespace {
 
-constexpr int SEL_THREADS = 256;
+constexpr int ST = 512;            // threads per CTA
+constexpr int SW = ST / 32;        // warps
 constexpr int SEL_BINS = 2048;
 constexpr int NPASS = 6;
 __constant__ int c_shift[NPASS] = {53, 42, 31, 20, 9, 0};
@@ -40,297 +47,345 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
   return __longlong_as_double((long long)u);
 }
 
-// One MSD pass.  st->prefix holds the digits decided so far (bits above shift + bits), st->remaining the rank still to
-// be resolved inside that prefix (1-based: the `remaining`-th smallest of the matching keys).
-__global__ void __launch_bounds__(SEL_THREADS) k_sel_pass(const double* __restrict__ keys, long long n, int pass, int K,
-                                                          SelectState* __restrict__ st, unsigned int* __restrict__ hist,
-                                                          unsigned int* __restrict__ ticket, double* __restrict__ scalars) {
-  __shared__ unsigned int sh[SEL_BINS];
-  __shared__ unsigned int wsum[SEL_THREADS / 32];
-  __shared__ int s_last;
-  const int shift = c_shift[pass], bits = c_bits[pass], nb = 1 << bits;
-  for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) sh[i] = 0u;
-  __syncthreads();
-  const unsigned long long prefix = (pass == 0) ? 0ull : st->prefix;
-  const int hi = shift + bits;   // bits [hi, 64) are decided
-  // log-likelihoods of a live pool share their leading bits, so whole warps hit one bin in the early passes:
-  // aggregate equal digits inside the warp (match.any) and let one lane add the group's count
-  const long long n_up = (n + 31) / 32 * 32;
-  for (long long i = (long long)blockIdx.x * SEL_THREADS + threadIdx.x; i < n_up; i += (long long)gridDim.x * SEL_THREADS) {
-    unsigned int digit = 0xffffffffu;
-    if (i < n) {
-      const unsigned long long k = key_image(keys[i]);
-      if ((hi >= 64) || ((k >> hi) == (prefix >> hi))) digit = (unsigned int)(k >> shift) & (nb - 1);
-    }
-    const unsigned int grp = __match_any_sync(0xffffffffu, digit);
-    if (digit != 0xffffffffu && (threadIdx.x & 31) == (__ffs(grp) - 1)) atomicAdd(&sh[digit], (unsigned int)__popc(grp));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += SEL_THREADS)
-    if (sh[i]) atomicAdd(&hist[i], sh[i]);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // ---- last CTA: find the digit whose cumulative count reaches `remaining` ----
-  const unsigned int remaining = (pass == 0) ? (unsigned int)K : st->remaining;
-  constexpr int PER = SEL_BINS / SEL_THREADS;   // 8 consecutive bins per thread
-  unsigned int loc[PER], tot = 0;
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const int b = threadIdx.x * PER + q;
-    loc[q] = (b < nb) ? __ldcg(&hist[b]) : 0u;
-    tot += loc[q];
-  }
-  // exclusive block scan of tot
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  unsigned int incl = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) wsum[wrp] = incl;
-  __syncthreads();
-  unsigned int base = 0;
-  for (int w = 0; w < wrp; ++w) base += wsum[w];
-  unsigned int before = base + incl - tot;   // keys in bins below this thread's first bin
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const int b = threadIdx.x * PER + q;
-    if (b < nb && before < remaining && remaining <= before + loc[q]) {
-      // exactly one (thread, q) satisfies this
-      st->prefix = prefix | ((unsigned long long)b << shift);
-      st->remaining = remaining - before;
-      st->bin_count = loc[q];
-      if (pass == NPASS - 1) {
-        const unsigned long long kk = prefix | ((unsigned long long)b << shift);
-        scalars[1] = key_value(kk);          // the threshold: the K-th smallest log-likelihood
-        st->ties_needed = remaining - before;  // keys equal to the threshold that retire (>= 1)
-        st->ties_total = loc[q];               // keys equal to the threshold in the whole pool
-      }
-    }
-    before += loc[q];
-  }
-  __syncthreads();
-  // re-arm for the next pass / next round
-  for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0u;
-  if (threadIdx.x == 0) *ticket = 0u;
-}
-
-// Per-slice counts over the GLOBAL key array: cnt[s] = (# keys < thr, # keys == thr) of slice s.  Slices are
-// rank-aligned: rank r owns slices [r * spr, (r + 1) * spr), slice i of a rank covers its keys [i * SEL_SLICE, ...).
-// Non-local slices are only needed to order ties; when every key equal to the threshold retires they are skipped.
-__global__ void __launch_bounds__(SEL_THREADS) k_sel_count(const double* __restrict__ keys, long long Pl, int spr, int rank,
-                                                           const SelectState* __restrict__ st,
-                                                           const double* __restrict__ scalars, int2* __restrict__ cnt) {
-  __shared__ int sb[SEL_THREADS / 32], se[SEL_THREADS / 32];
-  const int s = blockIdx.x, r = s / spr, i = s % spr;
-  const bool local = (r == rank);
-  if (!local && st->ties_needed == st->ties_total) return;   // no tie ordering needed: nobody reads this slice's counts
-  const unsigned long long thr = st->prefix;   // image of the threshold: all comparisons are on the integer images, so
-                                               // they agree bit for bit with the radix passes (-0.0 / +0.0, NaNs)
-  const long long k0 = (long long)r * Pl + (long long)i * SEL_SLICE;
-  const long long k1 = min((long long)r * Pl + Pl, k0 + SEL_SLICE);
-  int below = 0, equal = 0;
-  for (long long k = k0 + threadIdx.x; k < k1; k += SEL_THREADS) {
-    const unsigned long long v = key_image(keys[k]);
-    below += (v < thr) ? 1 : 0;
-    equal += (v == thr) ? 1 : 0;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    below += __shfl_xor_sync(0xffffffffu, below, o);
-    equal += __shfl_xor_sync(0xffffffffu, equal, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    sb[threadIdx.x >> 5] = below;
-    se[threadIdx.x >> 5] = equal;
-  }
+// Grid-wide barrier on a monotonically increasing counter (never reset: every launch of an engine uses the same grid).
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    int b = 0, e = 0;
-    for (int w = 0; w < SEL_THREADS / 32; ++w) {
-      b += sb[w];
-      e += se[w];
-    }
-    cnt[s] = make_int2(b, e);
-  }
-}
-
-// Local slices: retire flags + index-ordered compaction of the retired slots into sidx[0, c), c -> count[0].
-__global__ void __launch_bounds__(SEL_THREADS) k_sel_flag(const double* __restrict__ keys, long long Pl, int spr, int rank,
-                                                          const SelectState* __restrict__ st,
-                                                          const double* __restrict__ scalars, const int2* __restrict__ cnt,
-                                                          unsigned char* __restrict__ flags, int* __restrict__ sidx,
-                                                          int* __restrict__ count) {
-  __shared__ long long s_tie_base;   // keys == thr at lower global index than this slice
-  __shared__ int s_ret_base;         // retired points in earlier local slices
-  __shared__ int wsum[SEL_THREADS / 32];
-  const int i = blockIdx.x, s = rank * spr + i;
-  const unsigned long long thr = st->prefix;
-  const long long need = st->ties_needed;
-  const bool all_ties = st->ties_needed == st->ties_total;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  if (wrp == 0) {
-    // one warp walks the earlier slices in order (a few hundred entries)
-    long long tb = 0;
-    if (!all_ties)
-      for (int q = lane; q < s; q += 32) tb += cnt[q].y;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o);
-    // retired in earlier LOCAL slices: below + the ties taken there (needs each slice's own tie base: serial, lane 0)
-    int rb = 0;
-    if (all_ties) {
-      for (int q = lane; q < i; q += 32) rb += cnt[rank * spr + q].x + cnt[rank * spr + q].y;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rb += __shfl_xor_sync(0xffffffffu, rb, o);
-    } else if (lane == 0) {
-      long long t = 0;
-      for (int q = 0; q < rank * spr; ++q) t += cnt[q].y;
-      for (int q = 0; q < i; ++q) {
-        const int2 c = cnt[rank * spr + q];
-        long long take = need - t;
-        take = take < 0 ? 0 : (take > c.y ? c.y : take);
-        rb += c.x + (int)take;
-        t += c.y;
-      }
-    }
-    if (lane == 0) {
-      s_tie_base = tb;
-      s_ret_base = rb;
-    }
+    __threadfence();
+    const unsigned int ticket = atomicAdd(bar, 1u);
+    const unsigned int target = (ticket / nblocks + 1u) * nblocks;
+    while ((int)(*(volatile unsigned int*)bar - target) < 0) __nanosleep(32);
+    __threadfence();
   }
   __syncthreads();
-  constexpr int PER = SEL_SLICE / SEL_THREADS;   // 8 consecutive keys per thread
-  const long long l0 = (long long)i * SEL_SLICE + (long long)threadIdx.x * PER;   // local index of this thread's first key
-  unsigned long long v[PER];
-  int nt = 0;
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const long long l = l0 + q;
-    v[q] = (l < Pl) ? key_image(keys[(long long)rank * Pl + l]) : ~0ull;
-    nt += (l < Pl && v[q] == thr) ? 1 : 0;
-  }
-  // exclusive scan of the tie counts -> which ties are taken
-  auto block_excl = [&](int x) -> int {
-    int incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    __syncthreads();
-    if (lane == 31) wsum[wrp] = incl;
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < wrp; ++w) base += wsum[w];
-    return base + incl - x;
-  };
-  long long tie_rank = s_tie_base + (all_ties ? 0 : block_excl(nt));
-  bool ret[PER];
-  int nr = 0;
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const long long l = l0 + q;
-    bool r = false;
-    if (l < Pl) {
-      if (v[q] < thr) r = true;
-      else if (v[q] == thr) {
-        r = all_ties || (tie_rank < need);
-        ++tie_rank;
-      }
-    }
-    ret[q] = r;
-    nr += r ? 1 : 0;
-  }
-  int pos = s_ret_base + block_excl(nr);
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const long long l = l0 + q;
-    if (l < Pl) {
-      flags[l] = ret[q] ? 1 : 0;
-      if (ret[q]) sidx[pos++] = (int)l;
-    }
-  }
-  if (i == spr - 1 && threadIdx.x == SEL_THREADS - 1) count[0] = pos;   // the last thread of the last slice ends at c
 }
 
-// The retired VALUES of the round (every key below the threshold plus ties_needed copies of it), unordered: they are
-// sorted afterwards on the evidence stream, off the critical path.  One warp-aggregated atomic per warp.
-__global__ void __launch_bounds__(SEL_THREADS) k_sel_gather_values(const double* __restrict__ keys, long long n,
-                                                                   const SelectState* __restrict__ st,
-                                                                   const double* __restrict__ scalars, int Kr,
-                                                                   double* __restrict__ out, unsigned int* __restrict__ cursor) {
-  const unsigned long long thrk = st->prefix;
-  const double thr = scalars[1];
-  const int lane = threadIdx.x & 31;
-  const long long stride = (long long)gridDim.x * SEL_THREADS;
+// exclusive block scan of one int per thread (ST threads); sh: [SW] scratch
+__device__ __forceinline__ int block_excl_int(int x, int* sh, int* total) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  int incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();
+  if (lane == 31) sh[wrp] = incl;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SW; ++w) {
+    const int v = sh[w];
+    base += (w < wrp) ? v : 0;
+    tot += v;
+  }
+  if (total) *total = tot;
+  return base + incl - x;
+}
+
+struct SelectArgs {
+  const double* keys;   // [world * Pl] rank-major
+  long long Pl;
+  int world, rank, K, spr;
+  SelectBuffers b;
+  double* vals;         // [K] retired values, unordered
+};
+
+__global__ void __launch_bounds__(ST, 1) k_slq_select(const SelectArgs a) {
+  __shared__ unsigned int sh[SEL_BINS];
+  __shared__ int ssc[SW];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_remaining, s_bin;
+  __shared__ long long s_tie_base;
+  __shared__ int s_ret_base;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const unsigned int G = gridDim.x;
+  const long long n = a.Pl * a.world;
   const long long n_up = (n + 31) / 32 * 32;
-  for (long long i = (long long)blockIdx.x * SEL_THREADS + threadIdx.x; i < n_up; i += stride) {
-    const bool take = (i < n) && (key_image(keys[i]) < thrk);
-    const unsigned int m = __ballot_sync(0xffffffffu, take);
-    if (m) {
-      unsigned int base = 0;
-      if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (take) {
-        const unsigned int p = base + __popc(m & ((1u << lane) - 1u));
-        if (p < (unsigned int)Kr) out[p] = keys[i];
-      }
+  unsigned int* bar = a.b.ticket;
+
+  // ================= MSD radix passes =================
+  // Up to RK keys per thread stay in registers for all six passes (10^6 keys on 148 x 512 threads: 14 per thread), so a
+  // pass costs its histogram updates and one grid barrier, not another trip to L2; larger pools stream from memory with
+  // four independent loads in flight per thread.
+  constexpr int RK = 16;
+  const bool in_regs = n <= (long long)G * ST * RK;
+  unsigned long long kr[RK];
+  if (in_regs) {
+#pragma unroll
+    for (int q = 0; q < RK; ++q) {
+      const long long i = ((long long)q * G + blockIdx.x) * ST + threadIdx.x;
+      kr[q] = (i < n) ? key_image(a.keys[i]) : 0ull;
     }
   }
-  if (blockIdx.x == 0) {
-    const unsigned int need = st->ties_needed;
-    unsigned int base = 0;
-    if (threadIdx.x == 0) base = atomicAdd(cursor, need);
-    __shared__ unsigned int sb;
-    if (threadIdx.x == 0) sb = base;
+  unsigned long long prefix = 0ull;
+  unsigned int remaining = (unsigned int)a.K, bin_count = 0u;
+  for (int pass = 0; pass < NPASS; ++pass) {
+    const int shift = c_shift[pass], bits = c_bits[pass], nb = 1 << bits, hi = shift + bits;
+    unsigned int* hist = a.b.hist + pass * SEL_BINS;
+    for (int i = threadIdx.x; i < SEL_BINS; i += ST) sh[i] = 0u;
     __syncthreads();
-    base = sb;
-    for (unsigned int t = threadIdx.x; t < need; t += SEL_THREADS)
-      if (base + t < (unsigned int)Kr) out[base + t] = thr;
+    auto tally = [&](bool valid, unsigned long long k) {   // whole warp calls this together
+      unsigned int digit = 0xffffffffu;
+      if (valid && ((hi >= 64) || ((k >> hi) == (prefix >> hi)))) digit = (unsigned int)(k >> shift) & (nb - 1);
+      const unsigned int grp = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xffffffffu && lane == (__ffs(grp) - 1)) atomicAdd(&sh[digit], (unsigned int)__popc(grp));
+    };
+    if (in_regs) {
+#pragma unroll
+      for (int q = 0; q < RK; ++q) {
+        const long long i = ((long long)q * G + blockIdx.x) * ST + threadIdx.x;
+        if (((long long)q * G + blockIdx.x) * ST < n) tally(i < n, kr[q]);   // warp-uniform guard
+      }
+    } else {
+      const long long stride = (long long)G * ST;
+      for (long long i0 = (long long)blockIdx.x * ST + threadIdx.x; i0 - threadIdx.x < n_up; i0 += 4 * stride) {
+        unsigned long long k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          k4[u] = (i < n) ? key_image(a.keys[i]) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          if (i - threadIdx.x < n_up) tally(i < n, k4[u]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += ST)
+      if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    grid_barrier(bar, G);
+    // every CTA finds the digit whose cumulative count reaches `remaining` (same data, same answer)
+    constexpr int PER = SEL_BINS / ST;   // 4 consecutive bins per thread
+    unsigned int loc[PER];
+    int tot = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int bq = threadIdx.x * PER + q;
+      loc[q] = (bq < nb) ? __ldcg(&hist[bq]) : 0u;
+      tot += (int)loc[q];
+    }
+    unsigned int before = (unsigned int)block_excl_int(tot, ssc, nullptr);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int bq = threadIdx.x * PER + q;
+      if (bq < nb && before < remaining && remaining <= before + loc[q]) {   // exactly one (thread, q)
+        s_prefix = prefix | ((unsigned long long)bq << shift);
+        s_remaining = remaining - before;
+        s_bin = loc[q];
+      }
+      before += loc[q];
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    remaining = s_remaining;
+    bin_count = s_bin;
+    __syncthreads();
   }
-}
+  // prefix = image of the K-th smallest key; `remaining` of the `bin_count` keys equal to it retire
+  const unsigned long long thr = prefix;
+  const long long need = remaining;
+  const bool all_ties = remaining == bin_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.b.scalars[1] = key_value(thr);
+    a.b.state->prefix = thr;
+    a.b.state->remaining = remaining;
+    a.b.state->bin_count = bin_count;
+    a.b.state->ties_needed = remaining;
+    a.b.state->ties_total = bin_count;
+  }
 
-__global__ void k_sel_reset_cursor(unsigned int* cursor) { *cursor = 0u; }
+  // ================= per-slice counts + retired values =================
+  // A CTA takes its slices four at a time (thread t holds keys [4t, 4t+4) of each): all loads of a batch are in flight
+  // together, the four (below, equal) pairs are reduced side by side, and the batch reserves its stretch of the
+  // retired-value buffer with ONE atomic (order inside the buffer is irrelevant: it is sorted afterwards).
+  const int nslices = a.spr * a.world;
+  constexpr int SB = 4, KPT = SEL_SLICE / ST;   // slices per batch; keys per thread per slice
+  int* shi = reinterpret_cast<int*>(sh);        // [SB][2][SW] warp partials, then [SB] slice bases
+  for (int s0 = blockIdx.x * SB; s0 < nslices; s0 += (int)G * SB) {
+    double kv[SB][KPT];
+    bool tk[SB][KPT];
+    int below[SB], equal[SB];
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int s = s0 + u;
+      const int r = s / a.spr, i = s % a.spr;
+      const long long k0 = (long long)r * a.Pl + (long long)i * SEL_SLICE + (long long)threadIdx.x * KPT;
+      const long long k1 = (long long)r * a.Pl + a.Pl;
+#pragma unroll
+      for (int q = 0; q < KPT; ++q) {
+        const bool in = (s < nslices) && (k0 + q < k1) && ((long long)threadIdx.x * KPT + q < SEL_SLICE);
+        kv[u][q] = in ? a.keys[k0 + q] : 0.0;
+        tk[u][q] = in;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      below[u] = equal[u] = 0;
+#pragma unroll
+      for (int q = 0; q < KPT; ++q) {
+        const unsigned long long v = key_image(kv[u][q]);
+        equal[u] += (tk[u][q] && v == thr) ? 1 : 0;
+        tk[u][q] = tk[u][q] && v < thr;
+        below[u] += tk[u][q] ? 1 : 0;
+      }
+    }
+    // in-thread -> warp -> CTA exclusive offsets of the values to append (all SB slices of the batch as one run)
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < SB; ++u) mine += below[u];
+    int run_total = 0;
+    const int my_off = block_excl_int(mine, ssc, &run_total);
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      int b = below[u], e = equal[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+      }
+      if (lane == 0) {
+        shi[(u * 2 + 0) * SW + wrp] = b;
+        shi[(u * 2 + 1) * SW + wrp] = e;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < SB) {
+      const int u = threadIdx.x;
+      int bsum = 0, esum = 0;
+      for (int w = 0; w < SW; ++w) {
+        bsum += shi[(u * 2 + 0) * SW + w];
+        esum += shi[(u * 2 + 1) * SW + w];
+      }
+      if (s0 + u < nslices) a.b.cnt[s0 + u] = make_int2(bsum, esum);
+    }
+    if (threadIdx.x == 0) s_bin = run_total > 0 ? atomicAdd(a.b.cursor, (unsigned int)run_total) : 0u;
+    __syncthreads();
+    unsigned int p = s_bin + (unsigned int)my_off;
+#pragma unroll
+    for (int u = 0; u < SB; ++u)
+#pragma unroll
+      for (int q = 0; q < KPT; ++q)
+        if (tk[u][q]) {
+          if (p < (unsigned int)a.K) a.vals[p] = kv[u][q];
+          ++p;
+        }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {   // the ties that go, as values
+    __syncthreads();
+    if (threadIdx.x == 0) sh[0] = atomicAdd(a.b.cursor, (unsigned int)need);
+    __syncthreads();
+    const unsigned int base = sh[0];
+    const double tv = key_value(thr);
+    for (unsigned int t = threadIdx.x; t < (unsigned int)need; t += ST)
+      if (base + t < (unsigned int)a.K) a.vals[base + t] = tv;
+  }
+  grid_barrier(bar, G);
+
+  // ================= retire flags + ordered compaction (local slices) =================
+  for (int i = blockIdx.x; i < a.spr; i += (int)G) {
+    const int s = a.rank * a.spr + i;
+    __syncthreads();
+    if (wrp == 0) {
+      long long tb = 0;
+      int rb = 0;
+      if (all_ties) {
+        for (int q = lane; q < i; q += 32) {
+          const int2 c = __ldcg(&a.b.cnt[a.rank * a.spr + q]);
+          rb += c.x + c.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rb += __shfl_xor_sync(0xffffffffu, rb, o);
+      } else {
+        for (int q = lane; q < s; q += 32) tb += __ldcg(&a.b.cnt[q]).y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tb += __shfl_xor_sync(0xffffffffu, tb, o);
+        if (lane == 0) {   // ties taken in earlier local slices depend on each slice's own tie base: serial
+          long long t = 0;
+          for (int q = 0; q < a.rank * a.spr; ++q) t += __ldcg(&a.b.cnt[q]).y;
+          for (int q = 0; q < i; ++q) {
+            const int2 c = __ldcg(&a.b.cnt[a.rank * a.spr + q]);
+            long long take = need - t;
+            take = take < 0 ? 0 : (take > c.y ? c.y : take);
+            rb += c.x + (int)take;
+            t += c.y;
+          }
+        }
+      }
+      if (lane == 0) {
+        s_tie_base = tb;
+        s_ret_base = rb;
+      }
+    }
+    __syncthreads();
+    constexpr int PER = SEL_SLICE / ST;   // 4 consecutive keys per thread
+    const long long l0 = (long long)i * SEL_SLICE + (long long)threadIdx.x * PER;
+    unsigned long long v[PER];
+    int nt = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const long long l = l0 + q;
+      v[q] = (l < a.Pl) ? key_image(a.keys[(long long)a.rank * a.Pl + l]) : ~0ull;
+      nt += (l < a.Pl && v[q] == thr) ? 1 : 0;
+    }
+    long long tie_rank = s_tie_base + (all_ties ? 0 : block_excl_int(nt, ssc, nullptr));
+    bool ret[PER];
+    int nr = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const long long l = l0 + q;
+      bool r = false;
+      if (l < a.Pl) {
+        if (v[q] < thr) r = true;
+        else if (v[q] == thr) {
+          r = all_ties || (tie_rank < need);
+          ++tie_rank;
+        }
+      }
+      ret[q] = r;
+      nr += r ? 1 : 0;
+    }
+    int tot = 0;
+    int pos = s_ret_base + block_excl_int(nr, ssc, &tot);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const long long l = l0 + q;
+      if (l < a.Pl) {
+        a.b.flags[l] = ret[q] ? 1 : 0;
+        if (ret[q]) a.b.sidx[pos++] = (int)l;
+      }
+    }
+    if (i == a.spr - 1 && threadIdx.x == 0) a.b.count[0] = s_ret_base + tot;   // retired local points
+  }
+  // ================= re-arm for the next round (all histogram reads are behind the barriers above) =================
+  for (int i = blockIdx.x * ST + threadIdx.x; i < NPASS * SEL_BINS; i += (int)G * ST) a.b.hist[i] = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.b.cursor = 0u;
+}
 
 }  // namespace
 
 int slq_select_slices(long long Pl) { return (int)((Pl + SEL_SLICE - 1) / SEL_SLICE); }
 
-// keys: the GLOBAL key array (world * Pl entries, rank-major); selects the K lowest, writes the threshold to scalars[1],
-// this rank's retire flags / compacted slots / count.  8 launches, no host interaction, graph-capturable.
+// keys: the GLOBAL key array (world * Pl entries, rank-major).  Selects the K lowest: threshold -> scalars[1], the retired
+// values (unordered) -> vals[0, K), this rank's retire flags / compacted slots / count.  One cooperative launch, no host
+// interaction, graph-capturable.
 thy_status slq_select_launch(const SelectBuffers& b, const double* keys, long long Pl, int world, int rank, int K,
-                             cudaStream_t s) {
-  const long long n = Pl * world;
-  int grid = sm_count() * 2;
-  const long long need = (n + SEL_THREADS - 1) / SEL_THREADS;
-  if (grid > need) grid = (int)need;
-  if (grid < 1) grid = 1;
-  for (int pass = 0; pass < NPASS; ++pass)
-    k_sel_pass<<<grid, SEL_THREADS, 0, s>>>(keys, n, pass, K, b.state, b.hist, b.ticket, b.scalars);
-  const int spr = slq_select_slices(Pl);
-  k_sel_count<<<spr * world, SEL_THREADS, 0, s>>>(keys, Pl, spr, rank, b.state, b.scalars, b.cnt);
-  k_sel_flag<<<spr, SEL_THREADS, 0, s>>>(keys, Pl, spr, rank, b.state, b.scalars, b.cnt, b.flags, b.sidx, b.count);
-  count_launch(NPASS + 2);
-  THY_CUDA_CHECK(cudaGetLastError());
-  return THY_OK;
-}
-
-// Unordered retired values of the round into out[0, Kr) (evidence stream).
-thy_status slq_gather_retired_values(const SelectBuffers& b, const double* keys, long long n, int Kr, double* out,
-                                     cudaStream_t s) {
-  k_sel_reset_cursor<<<1, 1, 0, s>>>(b.cursor);
-  int grid = sm_count();
-  const long long need = (n + SEL_THREADS - 1) / SEL_THREADS;
-  if (grid > need) grid = (int)need;
-  if (grid < 1) grid = 1;
-  k_sel_gather_values<<<grid, SEL_THREADS, 0, s>>>(keys, n, b.state, b.scalars, Kr, out, b.cursor);
-  count_launch(2);
-  THY_CUDA_CHECK(cudaGetLastError());
+                             double* vals, cudaStream_t s) {
+  SelectArgs a{};
+  a.keys = keys;
+  a.Pl = Pl;
+  a.world = world;
+  a.rank = rank;
+  a.K = K;
+  a.spr = slq_select_slices(Pl);
+  a.b = b;
+  a.vals = vals;
+  void* args[] = {(void*)&a};
+  THY_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_slq_select, dim3((unsigned)sm_count()), dim3(ST), args, 0, s));
+  count_launch();
   return THY_OK;
 }
 

@@ -16,6 +16,7 @@ from ._capi import check, lib, register
 _vp = C.c_void_p
 register("thy_comm_unique_id", C.c_int, [C.POINTER(C.c_ubyte)])
 register("thy_comm_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(_vp)])
+register("thy_comm_create_all", C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)])
 register("thy_comm_destroy", C.c_int, [_vp])
 register("thy_comm_rank", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)])
 register("thy_comm_all_reduce_sum", C.c_int, [_vp, _vp, C.c_int64, _vp])
@@ -62,6 +63,22 @@ class Communicator:
         check(self._lib.thy_comm_create(rank, world, uid, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def createAll(cls, devices) -> list:
+        """Single-process mode (``thy_comm_create_all``): one communicator per listed GPU of THIS process; use each from
+        its own host thread, bound with ``setDevice``."""
+        devices = list(devices)
+        n = len(devices)
+        arr = (C.c_int * n)(*devices)
+        handles = (_vp * n)()
+        check(lib().thy_comm_create_all(n, arr, handles))
+        out = []
+        for i in range(n):
+            c = object.__new__(cls)
+            c._lib, c.rank, c.world, c._h = lib(), i, n, _vp(handles[i])
+            out.append(c)
+        return out
+
     @staticmethod
     def uniqueId() -> bytes:
         buf = (C.c_ubyte * 128)()
@@ -95,3 +112,14 @@ class Communicator:
             self.close()
         except Exception:
             pass
+
+
+def deviceCount() -> int:
+    n = C.c_int()
+    check(lib().thy_device_count(C.byref(n)))
+    return n.value
+
+
+def setDevice(device: int) -> None:
+    """Bind the calling thread to a GPU (``thy_set_device``); handles created afterwards live there."""
+    check(lib().thy_set_device(device))

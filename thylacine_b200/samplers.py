@@ -29,6 +29,9 @@ register("thy_hmc_sample", C.c_int, [_vp, C.c_int, _dp, C.c_int])
 register("thy_hmc_sample_dev", C.c_int, [_vp, C.c_int, _vp, C.c_int])
 register("thy_hmc_stats", C.c_int, [_vp, _i64p, _i64p, _dp])
 register("thy_hmc_get_state", C.c_int, [_vp, _dp, _dp])
+register("thy_hmc_set_state", C.c_int, [_vp, _dp, C.c_uint64])
+register("thy_hmc_get_trajectory_counter", C.c_int, [_vp, C.POINTER(C.c_uint64)])
+register("thy_hmc_set_fused_steps", C.c_int, [_vp, C.c_int])
 register("thy_lfm_create", C.c_int, [_vp, C.c_void_p, C.c_int, C.c_uint64, _dp, C.POINTER(_vp)])
 register("thy_lfm_destroy", C.c_int, [_vp])
 register("thy_lfm_run_sweeps", C.c_int, [_vp, C.c_int])
@@ -71,7 +74,7 @@ class HmcmcSampledPosterior:
 
     def __init__(self, hmcmcConfig: HmcmcConfig, posterior: UnnormalisedPosterior,
                  telemetryUpdateCallback: Optional[Callable[[HmcmcTelemetryUpdate], None]] = None,
-                 seed=None, numberOfChains: int = 1, rngSeed: int = 0, useGraph: bool = True):
+                 seed=None, numberOfChains: int = 1, rngSeed: int = 0, useGraph: bool = True, fusedSteps: bool = True):
         self.posterior = posterior
         self.config = hmcmcConfig
         self.numberOfChains = int(numberOfChains)
@@ -92,6 +95,8 @@ class HmcmcSampledPosterior:
         self._h = h
         if not useGraph:
             check(self._lib.thy_hmc_set_use_graph(h, 0))
+        if not fusedSteps:
+            check(self._lib.thy_hmc_set_fused_steps(h, 0))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -125,6 +130,16 @@ class HmcmcSampledPosterior:
 
     def burnIn(self) -> None:
         check(self._lib.thy_hmc_burn_in(self._h))
+
+    def setState(self, x, trajectoryCounter: int) -> None:
+        """Resume from a checkpoint: positions (numberOfChains, d) + the trajectory counter that keys every draw."""
+        x = np.ascontiguousarray(_arr(x).reshape(self.numberOfChains, self.posterior.domainDimension))
+        check(self._lib.thy_hmc_set_state(self._h, _ptr(x), int(trajectoryCounter)))
+
+    def trajectoryCounter(self) -> int:
+        t = C.c_uint64()
+        check(self._lib.thy_hmc_get_trajectory_counter(self._h, C.byref(t)))
+        return int(t.value)
 
     def runTrajectories(self, n: int) -> None:
         check(self._lib.thy_hmc_run_trajectories(self._h, n))
@@ -283,8 +298,8 @@ SLQ_INTEGRAND = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 register("thy_slq_integrate", C.c_int, [_vp, SLQ_INTEGRAND, C.c_void_p, C.c_double, _dp, _dp, _dp])
 register("thy_slq_set_trace", C.c_int, [_vp, C.c_int])
 register("thy_slq_phase_times", C.c_int, [_vp, _dp, _i64p])
-SLQ_PHASES = ("pool_spread", "all_gather_keys", "radix_select_flags", "retired_values", "walk_adapt", "wait_quadrature",
-              "round_control")
+SLQ_PHASES = ("all_gather_keys", "radix_select_flags_values", "walk_adapt", "wait_quadrature", "round_control",
+              "pool_spread_side_stream", "graph_replay")
 
 
 @dataclass
