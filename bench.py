@@ -479,7 +479,10 @@ def run_ours(args):
                     "chains_per_gpu": CHAINS, "trajectories": ntraj, "leapfrog_steps_per_trajectory": L_STEPS,
                     "step_size": eps, "acceptance_rank0": float(acc.sum() / max(att.sum(), 1)),
                     "tflops_canonical_per_gpu": CHAINS * ntraj * L_STEPS * FLOPS_PER_EVAL / hsec / 1e12,
-                    "note": "fused leapfrog/Metropolis kernels + the fused DMMA gradient, one CUDA-graph launch per trajectory"}
+                    "kernel_path": post.lastKernelPath,
+                    "note": "one CUDA-graph launch per trajectory; leapfrog step = fused DMMA gradient + elementwise kick/drift kernels "
+                            "(at this size the library's cost model keeps the step out of the gradient kernel's output step: "
+                            "558 vs 547 us measured; short models -- config 1, collapsed -- run one launch per step)"}
         hmc.close()
     except Exception as e:  # the evals/s line must not be lost to the HMC leg
         hmc_line = {"error": repr(e)}

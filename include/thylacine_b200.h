@@ -89,6 +89,9 @@ typedef enum thy_link {
   THY_LINK_SOFTPLUS = 4, THY_LINK_SIGMOID = 5
 } thy_link;
 
+/* Link ids >= THY_LINK_USER_BASE are user-defined families registered on a model with thy_model_register_link. */
+#define THY_LINK_USER_BASE 100
+
 typedef enum thy_jacobian {
   THY_JAC_CONSTANT = 0,           /* LinearForwardModel.jacobianAt: the coefficient blocks (:65-71)            */
   THY_JAC_ANALYTIC = 1,           /* NonLinearForwardModel.of(evaluation, jacobian, ...) (:64-85): link'(z) A   */
@@ -110,6 +113,17 @@ typedef struct thy_likelihood_desc {
   const double* uncertainties;    /* [n]  Gaussian/Cauchy: confidence intervals (sigma = ci/2); Uniform: lowerBounds */
   double differential;            /* finite-difference step (NonLinearForwardModel.of(differential = ...))     */
 } thy_likelihood_desc;
+
+/* NonLinearForwardModel.of(evaluation = <closure>, ...) (forwardmodel/NonLinearForwardModel.scala:44-85) for a family the
+ * registry above does not hold: the link -- f(theta)_i = link((A theta + offset)_i) -- as CUDA C source, an expression in
+ * the variable `z` (double), e.g. "z / (1.0 + fabs(z))"; deriv_expr is its derivative (z, and the value f = link(z), are in
+ * scope), e.g. "1.0 / ((1.0 + fabs(z)) * (1.0 + fabs(z)))", or NULL.  Compiled with NVRTC for sm_100a (THY_ERR_INVALID_ARGUMENT
+ * carries the compiler log; THY_ERR_UNSUPPORTED when libnvrtc.so.12 cannot be loaded) into the element-wise step between
+ * the two tensor-core GEMMs of the wide path.  *out_link is the id to put in thy_likelihood_desc.link of likelihoods added
+ * to THIS model afterwards.  With THY_JAC_ANALYTIC the derivative expression is required; with THY_JAC_FINITE_DIFFERENCE
+ * the link's own forward difference (link(z + h) - link(z)) / h, h = differential, stands in for it
+ * (core/computation/FiniteDifferenceJacobian.scala:30-55 has the same limit for this family).  Gaussian / Cauchy only. */
+thy_status thy_model_register_link(thy_model_t m, const char* eval_expr, const char* deriv_expr, int* out_link);
 
 /* GaussianLinearLikelihood.of / GaussianLikelihood.apply / CauchyLikelihood.apply,.of / UniformLikelihood.apply
  *   components/likelihood/{GaussianLinearLikelihood.scala:62-83, GaussianLikelihood.scala:55-67,
@@ -228,11 +242,12 @@ thy_status thy_hmc_get_state(thy_hmc_t h, double* out_x, double* out_logp);
  * which the chains continue exactly as the run that was checkpointed (same handle configuration and rng_seed). */
 thy_status thy_hmc_set_state(thy_hmc_t h, const double* x, uint64_t trajectory_counter);
 thy_status thy_hmc_get_trajectory_counter(thy_hmc_t h, uint64_t* out_counter);
-/* 1 (default): when the posterior is one fused-DMMA launch (single linear term + per-coordinate priors) every leapfrog
- * step is ONE kernel -- the gradient kernel's output step applies the momentum kicks and the drift, and on the last step
- * the Hamiltonian, the Metropolis test and the state update (HmcmcEngine.scala:55-172).  0: separate elementwise kernels
- * around the gradient evaluation (always used for models outside that shape). */
-thy_status thy_hmc_set_fused_steps(thy_hmc_t h, int enable);
+/* When the posterior is one fused-DMMA launch (single linear term + per-coordinate priors) a leapfrog step can be ONE
+ * kernel: the gradient kernel's output step applies the momentum kicks and the drift, and on the last step the
+ * Hamiltonian, the Metropolis test and the state update (HmcmcEngine.scala:55-172).  mode 2: always do that; 1 (default):
+ * when the cost model says it is faster (short gradient kernels: config 1, collapsed models); 0: separate elementwise
+ * kernels around the gradient evaluation (always used for models outside that shape). */
+thy_status thy_hmc_set_fused_steps(thy_hmc_t h, int mode);
 
 /* ---- Leapfrog MCMC (gradient-free ensemble sampler) -----------------------------------------------
  * LeapfrogMcmcSampledPosterior.of(leapfrogMcmcConfig, distanceCalculation, posterior, setCb, updateCb, seed)

@@ -62,6 +62,26 @@ def test_reference_assertions_become_status_codes(built_lib):
     assert e.value.status == _capi.THY_ERR_INVALID_ARGUMENT
 
 
+def test_user_links_compile_without_a_gpu_and_report_compiler_errors(built_lib):
+    """thy_model_register_link (NonLinearForwardModel.of(evaluation = closure) as CUDA source): NVRTC needs no device, so
+    registration -- and its error reporting, thread-local and handle-local -- is testable here."""
+    import thylacine_b200 as t
+    from thylacine_b200 import _capi
+    L = t.lib()
+    h = C.c_void_p()
+    _capi.check(L.thy_model_create(C.byref(h)))
+    out = C.c_int()
+    assert L.thy_model_register_link(h, b"z / (1.0 + fabs(z))", b"1.0 / ((1.0 + fabs(z)) * (1.0 + fabs(z)))", C.byref(out)) == 0
+    assert out.value == _capi.LINK_USER_BASE
+    assert L.thy_model_register_link(h, b"exp(-z * z)", None, C.byref(out)) == 0 and out.value == _capi.LINK_USER_BASE + 1
+    assert L.thy_model_register_link(h, b"no_such_function(z)", None, C.byref(out)) == _capi.THY_ERR_INVALID_ARGUMENT
+    assert b"no_such_function" in L.thy_last_error()
+    buf = C.create_string_buffer(2048)
+    assert L.thy_model_last_error(h, buf, 2048) == 0 and b"no_such_function" in buf.value   # handle-local copy
+    assert L.thy_model_register_link(h, b"", None, C.byref(out)) == _capi.THY_ERR_INVALID_ARGUMENT
+    L.thy_model_destroy(h)
+
+
 def test_no_cpu_fallback(built_lib):
     """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
     import torch

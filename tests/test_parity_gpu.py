@@ -300,6 +300,54 @@ def test_full_size_config2_properties():
     assert np.max(np.abs(g + D @ lam)) < 1e-9 * gscale                        # grad = -Lambda (x - mu)
 
 
+# ---- user-defined links compiled with NVRTC (NonLinearForwardModel.of(evaluation = closure)) ----------------------------
+@pytest.mark.parametrize("d,n,B", [(7, 60, 33), (200, 256, 300), (64, 5, 1), (129, 700, 130)])
+def test_user_link_matches_the_oracle_closure_and_the_registry(d, n, B):
+    """thy_model_register_link: a softsign family given as CUDA source runs between the two DMMA GEMMs of the wide path
+    and must agree with the oracle's NonLinearForwardModel built from the same function as Python closures
+    (NonLinearForwardModel.scala:44-85, analytic Jacobian overload :64-85); the registry's tanh re-registered as a user link
+    must reproduce the built-in family bit for bit (same expression, same kernels either side)."""
+    rng = np.random.default_rng(d + n)
+    A = rng.standard_normal((n, d)) / np.sqrt(d)
+    off = 0.1 * rng.standard_normal(n)
+    y = 0.5 * rng.standard_normal(n)
+    ci = np.full(n, 0.4)
+    pm, pci = np.zeros(d), np.full(d, 4.0)
+    X = 0.7 * rng.standard_normal((B, d))
+    soft = t.UserLink("z / (1.0 + fabs(z))", "1.0 / ((1.0 + fabs(z)) * (1.0 + fabs(z)))")
+    fm = t.NonLinearForwardModel.of(soft, {"w": A}, vectorOffset=off)
+    post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", pm, pci)], [t.CauchyLikelihood(fm, y, ci)],
+                                   cauchyReferenceSign=True)
+    f = lambda p: (A @ p["w"] + off) / (1.0 + np.abs(A @ p["w"] + off))
+    jac = lambda p: {"w": A / ((1.0 + np.abs(A @ p["w"] + off)) ** 2)[:, None]}
+    ofm = o.NonLinearForwardModel(f, None, {"w": d}, n, jacobian=jac)
+    ref = o.Posterior([o.gaussian_prior_from_ci("w", pm, pci)], [o.cauchy_likelihood(ofm, y, ci, True)])
+    lp, g = post.logPdfGradBatch(X)
+    assert post.lastKernelPath == "wide_dmma"
+    for b in range(min(B, 40)):
+        assert lp[b] == pytest.approx(ref.log_pdf(X[b]), rel=TOL)
+        assert rel_err_grad(g[b][None], ref.log_pdf_gradient(X[b])[None]) < TOL
+    assert rel_err_logp(post.logPdfBatch(X), lp) < 1e-14
+    # forward difference of the link itself when no derivative is given (same limit as FiniteDifferenceJacobian.scala:30-55)
+    fd = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", pm, pci)],
+                                 [t.CauchyLikelihood(t.NonLinearForwardModel.of(t.UserLink("z / (1.0 + fabs(z))"), {"w": A},
+                                                                                differential=1e-6, vectorOffset=off), y, ci)])
+    lp_fd, g_fd = fd.logPdfGradBatch(X)
+    assert np.array_equal(lp_fd, lp) and rel_err_grad(g_fd, g) < 1e-5
+    # the registry's tanh, re-registered as source
+    builtin = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", pm, pci)],
+                                      [t.GaussianLikelihood(t.NonLinearForwardModel.of("tanh", {"w": A}, vectorOffset=off), y, ci)],
+                                      kernelPath=capi.KERNEL_WIDE)
+    user = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("w", pm, pci)],
+                                   [t.GaussianLikelihood(t.NonLinearForwardModel.of(t.UserLink("tanh(z)", "1.0 - f * f"), {"w": A},
+                                                                                    vectorOffset=off), y, ci)])
+    lp_b, g_b = builtin.logPdfGradBatch(X)
+    lp_u, g_u = user.logPdfGradBatch(X)
+    assert np.array_equal(lp_b, lp_u) and np.array_equal(g_b, g_u)
+    for p_ in (post, fd, builtin, user):
+        p_.close()
+
+
 # ---- resident variant of the fused kernel: A held in shared memory for the CTA's lifetime ---------------------------
 RESIDENT_SHAPES = [(100, 100, 4096), (100, 100, 4099), (100, 104, 700), (10, 1000, 5000), (128, 128, 1200), (3, 250, 9000),
                    (64, 8, 333), (1, 1, 3000)]

@@ -8,7 +8,7 @@ from ._capi import ThylacineError, lib  # noqa: F401
 from . import _capi as capi  # noqa: F401
 from .api import (  # noqa: F401
     CauchyLikelihood, CauchyPrior, GaussianLikelihood, GaussianLinearLikelihood, GaussianPrior, LinearForwardModel,
-    NonLinearForwardModel, UniformLikelihood, UniformPrior, UnnormalisedPosterior, kernelLaunchCount,
+    NonLinearForwardModel, UniformLikelihood, UniformPrior, UnnormalisedPosterior, UserLink, kernelLaunchCount,
 )
 from .samplers import HmcmcConfig, HmcmcSampledPosterior, HmcmcTelemetryUpdate  # noqa: F401,E402
 from .samplers import LeapfrogMcmcConfig, LeapfrogMcmcSampledPosterior  # noqa: F401,E402

@@ -20,6 +20,7 @@ THY_ERR_INVALID_ARGUMENT, THY_ERR_UNKNOWN_LABEL, THY_ERR_CUDA, THY_ERR_NCCL = 1,
 THY_ERR_STATE, THY_ERR_UNSUPPORTED, THY_ERR_NO_DEVICE = 5, 6, 7
 
 DIST_GAUSSIAN, DIST_CAUCHY, DIST_UNIFORM = 0, 1, 2
+LINK_USER_BASE = 100
 LINK_IDENTITY, LINK_TANH, LINK_EXP, LINK_SQUARE, LINK_SOFTPLUS, LINK_SIGMOID = range(6)
 JAC_CONSTANT, JAC_ANALYTIC, JAC_FINITE_DIFFERENCE = 0, 1, 2
 OPT_CAUCHY_REFERENCE_SIGN, OPT_FD_INCREMENTAL, OPT_KERNEL_PATH, OPT_FUSE_PRIOR = 0, 1, 2, 3
@@ -69,6 +70,7 @@ SIGNATURES = {
     "thy_model_add_uniform_prior": (C.c_int, [_vp, C.c_char_p, C.c_int, _dp, _dp]),
     "thy_model_add_cauchy_prior": (C.c_int, [_vp, C.c_char_p, C.c_int, _dp, _dp]),
     "thy_model_add_likelihood": (C.c_int, [_vp, C.POINTER(LikelihoodDesc)]),
+    "thy_model_register_link": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]),
     "thy_model_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "thy_model_finalize": (C.c_int, [_vp]),
     "thy_model_dimension": (C.c_int, [_vp, C.POINTER(C.c_int)]),

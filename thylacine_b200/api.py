@@ -128,9 +128,20 @@ class LinearForwardModel:
         return LinearForwardModel.of(label, np.eye(dimension))
 
 
+@dataclass(frozen=True)
+class UserLink:
+    """A forward-model family the device registry does not hold, as CUDA C source in the variable ``z``
+    (``thy_model_register_link``: compiled with NVRTC for sm_100a when the posterior is built).  ``derivative`` is the
+    link's derivative (``z`` and ``f = link(z)`` in scope); omitted => pass ``differential`` to ``NonLinearForwardModel.of``
+    and the link's own forward difference is used.  Stands in for the reference's ``evaluation`` / ``jacobian`` closures
+    (NonLinearForwardModel.scala:44-85), which cannot run on a GPU."""
+    evaluation: str
+    derivative: Optional[str] = None
+
+
 class NonLinearForwardModel:
     @staticmethod
-    def of(link: str, coefficients: Mapping[str, Sequence], differential: Optional[float] = None, vectorOffset=None,
+    def of(link, coefficients: Mapping[str, Sequence], differential: Optional[float] = None, vectorOffset=None,
            domainDimensions: Optional[Mapping[str, int]] = None, rangeDimension: Optional[int] = None,
            evalCacheDepth=None, jacobianCacheDepth=None) -> _ForwardModel:
         """Device-registered family f(theta) = link(A . theta + offset).  ``differential`` given => the
@@ -144,9 +155,10 @@ class NonLinearForwardModel:
         if rangeDimension is not None:
             assert rows.copy().pop() == rangeDimension
         off = None if vectorOffset is None else _arr(vectorOffset)
+        code = link if isinstance(link, UserLink) else LINKS[link]   # a UserLink is resolved to an id by the posterior
         if differential is None:
-            return _ForwardModel(blocks, off, LINKS[link], _capi.JAC_ANALYTIC, 0.0)
-        return _ForwardModel(blocks, off, LINKS[link], _capi.JAC_FINITE_DIFFERENCE, float(differential))
+            return _ForwardModel(blocks, off, code, _capi.JAC_ANALYTIC, 0.0)
+        return _ForwardModel(blocks, off, code, _capi.JAC_FINITE_DIFFERENCE, float(differential))
 
 
 # ------------------------------------------------------------------------------------------ likelihoods
@@ -206,6 +218,7 @@ class UnnormalisedPosterior:
         h = C.c_void_p()
         check(L.thy_model_create(C.byref(h)))
         self._h = h
+        self._user_links: Dict[UserLink, int] = {}
         try:
             for p in priors:
                 lab = p.label.encode()
@@ -247,9 +260,17 @@ class UnnormalisedPosterior:
         dims = (C.c_int * nb)(*[fm.blocks[s].shape[1] for s in labels])
         mats = [np.ascontiguousarray(fm.blocks[s]) for s in labels]
         blk = (C.POINTER(C.c_double) * nb)(*[_ptr(m) for m in mats])
+        link = fm.link
+        if isinstance(link, UserLink):
+            if link not in self._user_links:
+                out = C.c_int()
+                check(self._lib.thy_model_register_link(self._h, link.evaluation.encode(),
+                                                        link.derivative.encode() if link.derivative else None, C.byref(out)))
+                self._user_links[link] = out.value
+            link = self._user_links[link]
         desc = _capi.LikelihoodDesc()
         desc.distribution = lk.distribution
-        desc.link = fm.link
+        desc.link = link
         desc.jacobian = fm.jacobian
         desc.n = fm.rangeDimension
         desc.nblocks = nb

@@ -13,6 +13,7 @@ static int select_path(thy_model_s* m, const LikDev& lk, int64_t B, bool want_gr
   const bool linear = (lk.link == THY_LINK_IDENTITY && lk.jacobian == THY_JAC_CONSTANT &&
                        lk.distribution != THY_DIST_UNIFORM);
   int path = m->opt_kernel_path;
+  if (lk.link >= THY_LINK_USER_BASE) return 4;   // NVRTC-compiled link: only the wide path has the hook
   if (path == 5) path = 2;   // 5 = fused DMMA, streaming variant only (launch_fused_dmma looks at the option itself)
   if (path == 2 && !(linear && fused_dmma_supported(lk, want_grad))) {
     *st = fail(THY_ERR_UNSUPPORTED, "fused DMMA kernel does not support this likelihood shape");

@@ -23,7 +23,7 @@ struct thy_hmc_s {
   thy::DevBuf<double> seed_points;                // [B][d] when provided
   thy::DevBuf<double> x, p, g, xn, gn;            // [B][d]; g, gn hold grad logp (not negated)
   thy::DevBuf<double> xn2;                        // second position buffer of the fused leapfrog step (ping-pong)
-  bool fused_steps = true;
+  int fused_steps = 1;                            // 0 never, 1 by cost model, 2 whenever the model allows it
   thy::DevBuf<double> lp, lpn, H0, dH;            // [B]
   thy::DevBuf<long long> attempts, acceptances, block_acc, emitted;  // [B]
   thy::DevBuf<unsigned long long> traj;           // [1] trajectory counter (device)
@@ -169,7 +169,17 @@ static thy_status hmc_trajectory_launch(thy_hmc_s* h) {
   k_hmc_begin<<<wblocks, 256, 0, s>>>(B, d, h->seed, h->traj.ptr, h->x.ptr, h->g.ptr, h->lp.ptr, h->p.ptr, h->xn.ptr,
                                       h->H0.ptr, eps);
   count_launch();
-  if (L > 0 && h->fused_steps && hmc_step_fusable(m, B)) {
+  // Folding the step into the gradient kernel saves the prior pass and the elementwise kick / drift kernel (two launches,
+  // ~64 bytes per coordinate of traffic) but makes the kernel's output step heavier, and the warps of a CTA reach that
+  // step together: measured on B200 the fused kernel is ~2 % slower than the plain one (config 2: 558 vs 547 us per
+  // step), so it wins while 2 % of the gradient kernel is less than the two small kernels it replaces (config 1 /
+  // collapsed models: 17 vs 19 us per step) -- fused_steps == 1 applies that rule, 2 forces the single launch.
+  bool fuse = L > 0 && h->fused_steps > 0 && hmc_step_fusable(m, B);
+  if (fuse && h->fused_steps == 1) {
+    const double t_small = 2 * 4e-6 + (double)B * d * 64.0 / 6e12;
+    fuse = 0.02 * fused_cost_model(m->lik_dev[0]->view, B) < t_small;
+  }
+  if (fuse) {
     // ONE launch per leapfrog step: kicks / drift / Metropolis test live in the gradient kernel's output step
     THY_TRY(h->xn2.reserve((size_t)B * d));
     double* cur = h->xn.ptr;
@@ -343,7 +353,7 @@ thy_status thy_hmc_destroy(thy_hmc_t h) {
 thy_status thy_hmc_set_fused_steps(thy_hmc_t h, int enable) {
   thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
-  h->fused_steps = enable != 0;
+  h->fused_steps = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   if (h->graph) {   // the captured trajectory belongs to the other mode
     cudaGraphExecDestroy(h->graph);
     h->graph = nullptr;

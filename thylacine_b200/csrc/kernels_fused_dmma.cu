@@ -96,40 +96,61 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
   const double* xrow = p.X + chain * p.d;
   const int mode = WANT_GRAD ? p.hmc.mode : 0;
   double* grow = WANT_GRAD ? p.grad + chain * p.d : nullptr;
+  double* prow = (WANT_GRAD && mode != HMC_FUSE_NONE) ? p.hmc.p + chain * p.d : nullptr;
   double acc = 0.0, kin = 0.0;
   bool inside = true;
   const double he = -p.hmc.eps / 2;
+  // Coordinates are taken in chunks of CH column pairs: all loads of a chunk are issued before anything depends on them
+  // (the warps of a CTA reach this step together, so its latency is not hidden by other warps' DMMAs).
+  constexpr int CH = 4;
 #pragma unroll
-  for (int t = 0; t < NT; ++t) {
+  for (int t0 = 0; t0 < NT; t0 += CH) {
+    double xv[CH][2], q0[CH][2], q1[CH][2], pm[CH][2];
+    int kd[CH][2];
+    bool ok[CH][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = 8 * t + 2 * q4 + h;
-      if (live && j < p.dl) {
-        const int kind = p.pr_kind[j];
-        const double xv = xrow[j];
+    for (int tt = 0; tt < CH; ++tt) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 8 * (t0 + tt) + 2 * q4 + h;
+        ok[tt][h] = live && (t0 + tt < NT) && j < p.dl;
+        xv[tt][h] = ok[tt][h] ? xrow[j] : 0.0;
+        kd[tt][h] = ok[tt][h] ? p.pr_kind[j] : -1;
+        q0[tt][h] = ok[tt][h] ? p.pr_p0[j] : 0.0;
+        q1[tt][h] = ok[tt][h] ? p.pr_p1[j] : 0.0;
+        pm[tt][h] = (ok[tt][h] && prow) ? prow[j] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < CH; ++tt) {
+      if (t0 + tt >= NT) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!ok[tt][h]) continue;
+        const int j = 8 * (t0 + tt) + 2 * q4 + h;
         double gj = 0.0;
-        if (kind == PK_GAUSS_DIAG) {
-          const double dl = p.pr_p0[j] - xv;
-          const double w = dl * p.pr_p1[j];
+        if (kd[tt][h] == PK_GAUSS_DIAG) {
+          const double dl = q0[tt][h] - xv[tt][h];
+          const double w = dl * q1[tt][h];
           acc += dl * w;
           gj = w;
-        } else if (kind == PK_UNIFORM) {
-          inside = inside && (xv >= p.pr_p0[j]) && (xv < p.pr_p1[j]);
+        } else if (kd[tt][h] == PK_UNIFORM) {
+          inside = inside && (xv[tt][h] >= q0[tt][h]) && (xv[tt][h] < q1[tt][h]);
         }
         if (WANT_GRAD) {
-          gj = gj + sc * ga[WANT_GRAD ? t : 0][h];
+          gj = gj + sc * ga[WANT_GRAD ? (t0 + tt) : 0][h];
           if (mode == HMC_FUSE_NONE) {
             grow[j] = gj;
           } else if (mode == HMC_FUSE_MID) {
             // second half kick of this leapfrog step, first half kick and drift of the next (HmcmcEngine.scala:55-80;
             // the reference works with -grad logp: p += (-g)(-eps/2), twice, then x += eps p)
             const double kick = __dmul_rn(-gj, he);
-            double pv = __dadd_rn(p.hmc.p[chain * p.d + j], kick);
+            double pv = __dadd_rn(pm[tt][h], kick);
             pv = __dadd_rn(pv, kick);
-            p.hmc.p[chain * p.d + j] = pv;
-            p.hmc.x_next[chain * p.d + j] = __dadd_rn(xv, __dmul_rn(pv, p.hmc.eps));
+            prow[j] = pv;
+            p.hmc.x_next[chain * p.d + j] = __dadd_rn(xv[tt][h], __dmul_rn(pv, p.hmc.eps));
           } else {
-            const double pv = __dadd_rn(p.hmc.p[chain * p.d + j], __dmul_rn(-gj, he));   // last half kick
+            const double pv = __dadd_rn(pm[tt][h], __dmul_rn(-gj, he));   // last half kick
             kin += pv * pv;
           }
         }
@@ -164,9 +185,9 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
           const int j = 8 * t + 2 * q4 + h;
           if (j < p.dl) {
             // the gradient is recomputed (same operations, same value) rather than kept in 2 NT more registers
-            const double xv = xrow[j];
-            const double gpr = (p.pr_kind[j] == PK_GAUSS_DIAG) ? (p.pr_p0[j] - xv) * p.pr_p1[j] : 0.0;
-            p.hmc.x[chain * p.d + j] = xv;
+            const double xj = xrow[j];
+            const double gpr = (p.pr_kind[j] == PK_GAUSS_DIAG) ? (p.pr_p0[j] - xj) * p.pr_p1[j] : 0.0;
+            p.hmc.x[chain * p.d + j] = xj;
             p.hmc.g[chain * p.d + j] = gpr + sc * ga[WANT_GRAD ? t : 0][h];
           }
         }
@@ -358,7 +379,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_fused_dmma(const FusedPara
 #pragma unroll
       for (int kk = 0; kk < C::KS; ++kk) {
         const int k = 4 * kk + q4;
-        xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + p.col[k]] : 0.0;
+        xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + (FUSE_PRIOR ? k : p.col[k])] : 0.0;
       }
       if (WANT_GRAD) {
 #pragma unroll
@@ -470,6 +491,7 @@ __device__ __forceinline__ void resident_rows(const double* __restrict__ As, con
   }
 }
 
+// (12 warps per CTA at 170 registers each were measured too: no faster at 65 536 chains, slower at 16 384.)
 template <int NT, bool WANT_GRAD, bool FUSE_PRIOR>
 __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams p) {
   using C = Cfg<NT>;
@@ -510,7 +532,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
 #pragma unroll
     for (int kk = 0; kk < C::KS; ++kk) {
       const int k = 4 * kk + q4;
-      xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + p.col[k]] : 0.0;
+      xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + (FUSE_PRIOR ? k : p.col[k])] : 0.0;
     }
     if (!loaded) {
       ptx::mbar_wait(bar, 0);
@@ -522,13 +544,20 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
       for (int t = 0; t < NT; ++t) ga[t][0] = ga[t][1] = 0.0;
     }
     double ssq = 0.0;
+    // row groups in balanced blocks of 4 / 3 (13 groups = 4 + 3 + 3 + 3, never 4 + 4 + 4 + 1: a block's groups are the
+    // independent accumulator chains of GEMM1, and a single chain leaves the DMMA pipe waiting on its own latency)
+    const int nblocks = (p.nrg + JG - 1) / JG, base = p.nrg / nblocks, extra = p.nrg % nblocks;
     int rg = 0;
-    for (; rg + JG <= p.nrg; rg += JG)
-      resident_rows<NT, JG, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
-    const int rem = p.nrg - rg;
-    if (rem == 3) resident_rows<NT, 3, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
-    else if (rem == 2) resident_rows<NT, 2, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
-    else if (rem == 1) resident_rows<NT, 1, WANT_GRAD>(As + (size_t)rg * 8 * C::LDS, Ys + rg * 8, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int cnt = base + (blk < extra ? 1 : 0);
+      const double* Ab = As + (size_t)rg * 8 * C::LDS;
+      const double2* Yb = Ys + rg * 8;
+      if (cnt == 4) resident_rows<NT, 4, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+      else if (cnt == 3) resident_rows<NT, 3, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+      else if (cnt == 2) resident_rows<NT, 2, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+      else resident_rows<NT, 1, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
+      rg += cnt;
+    }
     const double qsum = quad_sum(ssq);
     if (FUSE_PRIOR) {
       emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qsum, ga);
@@ -561,7 +590,7 @@ thy_status launch_resident_nt(thy_model_s* m, FusedParams& p, bool want_grad, cu
   int warps = (int)((ngroups + sms - 1) / sms);
   warps = warps < 1 ? 1 : (warps > NW ? NW : warps);
   if (warps == 3) warps = 4;
-  if (warps > 4 && warps < NW) warps = NW;
+  if (warps > 4) warps = NW;
   long long grid = (ngroups + warps - 1) / warps;
   if (grid > sms) grid = sms;
   KernelTimer timer(m, s);

@@ -306,7 +306,11 @@ __global__ void __launch_bounds__((WNW + 1) * 32, 1) k_wide_adj(const LikDev lk,
 
 }  // namespace
 
+// user links: THY_JAC_FINITE_DIFFERENCE means the link's own forward difference inside the compiled step
+static bool wide_user_link(const LikDev& lk) { return lk.link >= THY_LINK_USER_BASE; }
+
 bool wide_supported(const LikDev& lk) {
+  if (wide_user_link(lk)) return lk.distribution != THY_DIST_UNIFORM && lk.n >= 1 && lk.dl >= 1;
   return lk.distribution != THY_DIST_UNIFORM && lk.jacobian != THY_JAC_FINITE_DIFFERENCE && lk.n >= 1 && lk.dl >= 1;
 }
 
@@ -388,7 +392,11 @@ thy_status launch_wide_likelihood(thy_model_s* m, LikDevOwner& own, int64_t B, c
         k_wide_fwd<false><<<dim3(btiles, n_tiles), (WNW + 1) * 32, smem_f, s>>>(lk, p);
       timer.stop();
     }
-    if (!fused_epi) {
+    if (wide_user_link(lk)) {
+      UserLink& ul = *m->user_links[lk.link - THY_LINK_USER_BASE];
+      THY_TRY(user_link_launch(ul, p.WTl, lk.off, lk.yiv, p.partS, nb, lk.n, n_tiles, ictiles, p.write_deriv, lk.differential,
+                               WT, WK, WP, TILE_KC, s));
+    } else if (!fused_epi) {
       k_wide_link<<<(unsigned)ceil_div(nb * n_tiles, 8), 256, 0, s>>>(lk, p);
       count_launch();
     }

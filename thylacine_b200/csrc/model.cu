@@ -323,7 +323,19 @@ thy_status thy_model_add_likelihood(thy_model_t m, const thy_likelihood_desc* d)
   if (d->n <= 0 || d->nblocks <= 0) return fail(THY_ERR_INVALID_ARGUMENT, "n and nblocks must be positive");
   if (d->distribution < THY_DIST_GAUSSIAN || d->distribution > THY_DIST_UNIFORM)
     return fail(THY_ERR_INVALID_ARGUMENT, "unknown distribution");
-  if (d->link < THY_LINK_IDENTITY || d->link > THY_LINK_SIGMOID) return fail(THY_ERR_INVALID_ARGUMENT, "unknown link");
+  const bool user_link = d->link >= THY_LINK_USER_BASE && d->link < THY_LINK_USER_BASE + (int)m->user_links.size();
+  if (!user_link && (d->link < THY_LINK_IDENTITY || d->link > THY_LINK_SIGMOID))
+    return fail(THY_ERR_INVALID_ARGUMENT, "unknown link");
+  if (user_link) {
+    if (d->distribution == THY_DIST_UNIFORM)
+      return fail(THY_ERR_UNSUPPORTED, "user-defined links take Gaussian or Cauchy observations");
+    if (d->jacobian == THY_JAC_CONSTANT)
+      return fail(THY_ERR_INVALID_ARGUMENT, "a constant Jacobian requires the identity link (LinearForwardModel)");
+    if (d->jacobian == THY_JAC_ANALYTIC && !m->user_links[d->link - THY_LINK_USER_BASE]->has_deriv)
+      return fail(THY_ERR_INVALID_ARGUMENT, "THY_JAC_ANALYTIC needs a link registered with a derivative expression");
+    if (d->jacobian == THY_JAC_FINITE_DIFFERENCE && !(d->differential > 0))
+      return fail(THY_ERR_INVALID_ARGUMENT, "finite differences need a positive differential");
+  }
   if (d->jacobian < THY_JAC_CONSTANT || d->jacobian > THY_JAC_FINITE_DIFFERENCE)
     return fail(THY_ERR_INVALID_ARGUMENT, "unknown jacobian mode");
   if (d->jacobian == THY_JAC_CONSTANT && d->link != THY_LINK_IDENTITY)
@@ -367,6 +379,17 @@ thy_status thy_model_add_likelihood(thy_model_t m, const thy_likelihood_desc* d)
     THY_TRY(ci_to_var(d->uncertainties, d->n, L.unc));  // unc now holds variances
   }
   m->liks.push_back(std::move(L));
+  return THY_OK;
+}
+
+thy_status thy_model_register_link(thy_model_t m, const char* eval_expr, const char* deriv_expr, int* out_link) {
+  thy::ErrScope _err_scope(m);
+  THY_TRY(check_model(m, false));
+  if (!out_link) return fail(THY_ERR_INVALID_ARGUMENT, "null out pointer");
+  std::unique_ptr<UserLink> link;
+  THY_TRY(user_link_compile(eval_expr, deriv_expr, &link));
+  m->user_links.push_back(std::move(link));
+  *out_link = THY_LINK_USER_BASE + (int)m->user_links.size() - 1;
   return THY_OK;
 }
 

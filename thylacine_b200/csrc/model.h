@@ -1,6 +1,7 @@
 // Host-side model description and the POD device views handed to kernels.
 #pragma once
 #include "common.cuh"
+#include "user_link.h"
 #include <map>
 #include <memory>
 #include <mutex>
@@ -113,6 +114,7 @@ struct thy_model_s {
   cudaStream_t own_stream = nullptr;
   int device = -1;
   std::map<std::string, std::pair<int, int>> layout;  // label -> (offset, dim)
+  std::vector<std::unique_ptr<thy::UserLink>> user_links;  // thy_model_register_link: link id = THY_LINK_USER_BASE + index
   // device state
   thy::PriorDev prior_view{};
   thy::DevBuf<int> pr_kind;

@@ -74,7 +74,7 @@ class HmcmcSampledPosterior:
 
     def __init__(self, hmcmcConfig: HmcmcConfig, posterior: UnnormalisedPosterior,
                  telemetryUpdateCallback: Optional[Callable[[HmcmcTelemetryUpdate], None]] = None,
-                 seed=None, numberOfChains: int = 1, rngSeed: int = 0, useGraph: bool = True, fusedSteps: bool = True):
+                 seed=None, numberOfChains: int = 1, rngSeed: int = 0, useGraph: bool = True, fusedSteps=None):
         self.posterior = posterior
         self.config = hmcmcConfig
         self.numberOfChains = int(numberOfChains)
@@ -95,8 +95,8 @@ class HmcmcSampledPosterior:
         self._h = h
         if not useGraph:
             check(self._lib.thy_hmc_set_use_graph(h, 0))
-        if not fusedSteps:
-            check(self._lib.thy_hmc_set_fused_steps(h, 0))
+        if fusedSteps is not None:   # None: the library's cost model; True / False: always / never one launch per step
+            check(self._lib.thy_hmc_set_fused_steps(h, 2 if fusedSteps else 0))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A few evaluations of one named case, for `ncu` launch lists / full captures (see profiles/*.md).
 
-    python tools/profile_case.py --case c2|c3|c5_analytic|c5_fd|stream|slq [--reps 3]
+    python tools/profile_case.py --case c2|c3|c5_analytic|c5_fd|c5_fd_literal|stream|slq|collapsed|collapsed4k|hmc_c2|hmc_c1|lfm|moments [--reps 3]
 """
 import argparse
 import os
@@ -63,6 +63,42 @@ def main():
                                        [t.CauchyLikelihood(fm, y, np.full(n, 0.1))], fdIncremental=(args.case == "c5_fd"),
                                        cauchyReferenceSign=False)
         run(post, theta[None, :] + 0.05 * rng.standard_normal((B, d)))
+    elif args.case in ("collapsed", "collapsed4k"):
+        # config 2 collapsed onto d observations: the resident-A variant of the fused kernel (one launch per evaluation)
+        d, n, B = 100, 10_000, (65536 if args.case == "collapsed" else 4096)
+        A, theta, y = lin(d, n)
+        post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.full(d, 20.0))],
+                                       [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.2), "theta")])
+        col = post.collapsed()
+        run(col, theta[None, :] + 0.02 * rng.standard_normal((B, d)))
+    elif args.case in ("hmc_c2", "hmc_c1"):
+        d, n, B = (100, 10_000, 4096) if args.case == "hmc_c2" else (10, 1000, 4096)
+        A, theta, y = lin(d, n)
+        post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.full(d, 20.0))],
+                                       [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.2), "theta")])
+        cfg = t.HmcmcConfig(1, 4, 1, 0.2 * 0.1 * float(np.sqrt(d / n)))
+        hmc = t.HmcmcSampledPosterior(cfg, post, numberOfChains=B, rngSeed=1, seed={"theta": theta}, useGraph=False)
+        hmc.burnIn()
+        hmc.runTrajectories(args.reps)
+        post.synchronize()
+        print(args.case, post.lastKernelPath)
+    elif args.case == "lfm":
+        d, n, P = 100, 2000, 4096
+        A, theta, y = lin(d, n)
+        post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.full(d, 20.0))],
+                                       [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.2), "theta")])
+        lfm = t.LeapfrogMcmcSampledPosterior.of(t.LeapfrogMcmcConfig(1, 1, P), "euclidean", post, rngSeed=3)
+        lfm.runSweeps(args.reps)
+        post.synchronize()
+        print("lfm", post.lastKernelPath)
+    elif args.case == "moments":
+        d, n = 100, 200_000
+        post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.ones(d))])
+        mom = t.SampleMoments(post)
+        X = torch.from_numpy(rng.standard_normal((n, d))).cuda()
+        for _ in range(args.reps):
+            mom.add(X)
+        print("moments", mom.finish()[0])
     elif args.case == "slq":
         d, P = 50, 1_000_000
         y = rng.standard_normal(d)
