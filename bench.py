@@ -229,6 +229,8 @@ def run_slq_leg(t, torch, dist, rank, world, stream, barrier):
     sec = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
     st = slq.stats
     launches = t.kernelLaunchCount() - launches0
+    lb_mean, lb_max = slq.loadBalance()
+    lb_max_all = max_over_ranks(lb_max)
     H = st.neg_entropy_mean
     tol = 5.0 * math.sqrt(max(H, 0.0) / P) + 3.0 * st.log_evidence_std / math.sqrt(A)
     out = {
@@ -241,6 +243,7 @@ def run_slq_leg(t, torch, dist, rank, world, stream, barrier):
         "tolerance": tol, "within_tolerance": bool(abs(st.log_evidence_mean - want) < tol),
         "neg_entropy": H, "std_over_abscissas": st.log_evidence_std, "walk_acceptance": st.walk_acceptance,
         "gpu_launches": int(launches),
+        "replacements_per_round_per_rank": {"ideal": K / world, "rank0_mean": lb_mean, "max_over_ranks_and_rounds": lb_max_all},
         "collective": ("one NCCL all-gather of every rank's log-likelihoods per round on the product communicator "
                        "(thy_comm_create, not torch.distributed)" if world > 1 else "none (single rank)"),
     }

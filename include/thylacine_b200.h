@@ -275,6 +275,8 @@ thy_status thy_lfm_run_sweeps(thy_lfm_t h, int n_sweeps);
 thy_status thy_lfm_sample(thy_lfm_t h, int n, double* out_samples);
 thy_status thy_lfm_stats(thy_lfm_t h, uint64_t* out_proposals, uint64_t* out_acceptances);
 thy_status thy_lfm_get_pool(thy_lfm_t h, double* out_x, double* out_logp);
+/* Replace the pool (host [samplePoolSize * d]): warm start near the mode, or resume from thy_lfm_get_pool's output. */
+thy_status thy_lfm_set_pool(thy_lfm_t h, const double* x);
 
 /* ---- multi-GPU plumbing ---------------------------------------------------------------------------
  * The reference has no distributed layer (single JVM process).  Here: one process per GPU; chains, pool members and
@@ -367,6 +369,9 @@ thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* use
  * values; walk + adapt; wait for the quadrature stream; round control), mean microseconds per traced round; out_us[5] the
  * pool-spread kernels, which run on a side stream beside phases 0-1; out_us[6] = 1 when untraced full rounds replay from
  * a CUDA graph, else 0. */
+/* Load balance of the sharded live pool: mean and largest number of points THIS rank had to replace in one round (the
+ * K globally lowest points are wherever they are; a round lasts as long as its busiest rank's walk). */
+thy_status thy_slq_load_balance(thy_slq_t h, double* out_mean_local, double* out_max_local);
 thy_status thy_slq_set_trace(thy_slq_t h, int enable);
 thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_rounds);
 /* Per-abscissa ln Z_a and H_a of the quadrature so far (QuadratureIntegrator.scala:29-62); [abscissaNumber] each. */

@@ -42,6 +42,7 @@ private[thylacine] object ThylacineB200 {
   val addUniformPrior    = fn("thy_model_add_uniform_prior", I, P, P, I, P, P)          // UniformPrior.scala:68-77 (max, min)
   val addCauchyPrior     = fn("thy_model_add_cauchy_prior", I, P, P, I, P, P)           // CauchyPrior.scala:50-63
   val addLikelihood      = fn("thy_model_add_likelihood", I, P, P)                      // likelihood/*.scala
+  val registerLink       = fn("thy_model_register_link", I, P, P, P, P)                 // NonLinearForwardModel.scala:44-85 (closure -> CUDA source)
   val setOption          = fn("thy_model_set_option", I, P, I, I)
   val finalizeModel      = fn("thy_model_finalize", I, P)                               // Posterior.scala:40-48 label sort
   val collapse           = fn("thy_model_collapse", I, P, P)
@@ -90,6 +91,7 @@ private[thylacine] object ThylacineB200 {
   val lfmSample          = fn("thy_lfm_sample", I, P, I, P)
   val lfmStats           = fn("thy_lfm_stats", I, P, P, P)
   val lfmGetPool         = fn("thy_lfm_get_pool", I, P, P, P)
+  val lfmSetPool         = fn("thy_lfm_set_pool", I, P, P)
 
   // ---- multi-GPU plumbing (no counterpart in the reference: single JVM process, SURVEY 2a) --------------------------------
   val commUniqueId       = fn("thy_comm_unique_id", I, P)
@@ -122,6 +124,7 @@ private[thylacine] object ThylacineB200 {
   val slqAbscissaResults = fn("thy_slq_abscissa_results", I, P, P, P)                   // QuadratureIntegrator.scala:29-62
   val slqIntegrate       = fn("thy_slq_integrate", I, P, P, P, D, P, P, P)              // SlqEngine.scala:460-466
   val slqSample          = fn("thy_slq_sample", I, P, I, L, P)                          // SamplingSimulation.scala:41-101
+  val slqLoadBalance     = fn("thy_slq_load_balance", I, P, P, P)
   val slqSetTrace        = fn("thy_slq_set_trace", I, P, I)
   val slqPhaseTimes      = fn("thy_slq_phase_times", I, P, P, P)
 

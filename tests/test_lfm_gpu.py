@@ -27,33 +27,10 @@ def _model(d, n, seed, prior_sigma=0.3):
 
 
 def _host_sweep(x, lp, logpdf, seed, sweep, dist):
-    """The device's half-pool sweep restated on the host with the same counter-based draws."""
-    P = len(x)
-    n0 = P // 2
-    for half in (0, 1):
-        H = list(range(0, n0)) if half == 0 else list(range(n0, P))
-        S = list(range(n0, P)) if half == 0 else list(range(0, n0))
-        XS = x[S].copy()
-        updates = []
-        for i in H:
-            D = np.array([dist(x[i], s) for s in XS])
-            total = D.sum()
-            u = ph.uniform2(seed, i, 0, ph.RNG_LFM_PARTNER, sweep)[0]
-            cdf = np.cumsum(D)
-            j = int(np.searchsorted(cdf, u * total, side="right"))
-            j = min(j, len(S) - 1)
-            qf = D[j] / total
-            xp = 2.0 * XS[j] - x[i]
-            D2 = np.array([dist(xp, s) for s in XS])
-            qr = D2[j] / D2.sum()
-            lpp = logpdf(xp)
-            a = math.exp(min(lpp - lp[i], 700)) * qr / qf
-            ua = ph.uniform2(seed, i, 0, ph.RNG_LFM_ACCEPT, sweep)[0]
-            if a >= 1 or ua < a:
-                updates.append((i, xp, lpp))
-        for i, xp, lpp in updates:
-            x[i] = xp
-            lp[i] = lpp
+    """The device's half-pool sweep restated on the host (oracle/batched_restatements.py) with the same counter-based draws."""
+    from oracle.batched_restatements import leapfrog_mcmc_half_pool_sweep
+    leapfrog_mcmc_half_pool_sweep(x, lp, logpdf, lambda i: ph.uniform2(seed, i, 0, ph.RNG_LFM_PARTNER, sweep)[0],
+                                  lambda i: ph.uniform2(seed, i, 0, ph.RNG_LFM_ACCEPT, sweep)[0], dist)
 
 
 @pytest.mark.parametrize("distance", ["euclidean", "squared_euclidean", "manhattan"])

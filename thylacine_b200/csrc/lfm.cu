@@ -333,6 +333,18 @@ thy_status thy_lfm_stats(thy_lfm_t h, uint64_t* out_proposals, uint64_t* out_acc
   return THY_OK;
 }
 
+// Replace the whole pool (warm start near the mode, or a checkpointed pool): positions [samplePoolSize * d] from the
+// host; their log-posteriors are re-evaluated on the device.
+thy_status thy_lfm_set_pool(thy_lfm_t h, const double* x) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
+  if (!h || !x) return fail(THY_ERR_INVALID_ARGUMENT, "null pointer");
+  cudaStream_t s = h->model->stream;
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->x.ptr, x, (size_t)h->P * h->d * sizeof(double), cudaMemcpyHostToDevice, s));
+  THY_TRY(eval_batch_dev(h->model, h->P, h->x.ptr, h->lp.ptr, nullptr, true));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  return THY_OK;
+}
+
 thy_status thy_lfm_get_pool(thy_lfm_t h, double* out_x, double* out_logp) {
   thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");

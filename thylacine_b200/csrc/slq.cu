@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(1024) k_slq_adapt(double* scalars, double inc,
   }
   scalars[5] += acc;
   scalars[6] += prop;
+  scalars[2] = fmax(scalars[2], (double)c);   // load balance across ranks: largest / total local retire count so far
+  scalars[3] += (double)c;
 }
 
 // Copy retired points in the order of sidx (world == 1 with keepRetiredPoints: slots sorted by log-likelihood, i.e. the
@@ -730,6 +732,17 @@ thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_round
     if (out_us) out_us[i] = h->tcount > 0 ? 1e3 * h->tsum[i] / h->tcount : 0.0;
   if (out_us) out_us[6] = h->graph ? 1.0 : 0.0;   // 1 when untraced full rounds replay from a CUDA graph
   if (out_rounds) *out_rounds = h->tcount;
+  return THY_OK;
+}
+
+thy_status thy_slq_load_balance(thy_slq_t h, double* out_mean_local, double* out_max_local) {
+  thy::ErrScope _err_scope(h ? h->model : nullptr);
+  if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
+  double sc[8];
+  THY_CUDA_CHECK(cudaStreamSynchronize(h->model->stream));
+  THY_CUDA_CHECK(cudaMemcpy(sc, h->scalars.ptr, sizeof(sc), cudaMemcpyDeviceToHost));
+  if (out_mean_local) *out_mean_local = h->rounds > 0 ? sc[3] / (double)h->rounds : 0.0;
+  if (out_max_local) *out_max_local = sc[2];
   return THY_OK;
 }
 

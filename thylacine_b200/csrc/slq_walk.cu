@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
   const int pi_s1 = (q4 < 2) ? (2 * q4 + 1) : (2 * q4);
   const int off1 = pi_g * LDS + q4;
   const double thr = p.scalars[1];
-  const int ngrp = p.n_pad / 8;
+  const int ngrp = (p.n + 7) / 8;   // row groups that hold observations (rows beyond n are zero padding)
   const int d = p.d;
   const int c = *p.c_dev;
   const uint64_t round = (uint64_t)*p.round_dev;
@@ -135,6 +135,9 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
       const bool inside_all = ((ballot >> (lane & ~3)) & 0xFu) == 0xFu;
       const double lpn = inside_all ? (-0.5 * pacc + p.pr.log_const) : -INFINITY;
       // ---- forward pass on the tensor cores, residual quadratic form ----
+      // (Eight independent accumulator chains per block instead of two were measured and dropped: 1276 vs 1155 us per
+      // round at 62 500 walkers, 299 vs 284 us at 7 812 -- the step is bound by its ~1600 dependent scalar instructions,
+      // Philox and the prior test, not by the DMMA chain; profiles/r02_ncu_walk_low_occupancy.json.)
       double ssq = 0.0;
       for (int j = 0; j < ngrp; j += 2) {
         double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;

@@ -38,6 +38,7 @@ register("thy_lfm_run_sweeps", C.c_int, [_vp, C.c_int])
 register("thy_lfm_sample", C.c_int, [_vp, C.c_int, _dp])
 register("thy_lfm_stats", C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
 register("thy_lfm_get_pool", C.c_int, [_vp, _dp, _dp])
+register("thy_lfm_set_pool", C.c_int, [_vp, _dp])
 
 
 class _LeapfrogMcmcConfigC(C.Structure):
@@ -229,6 +230,11 @@ class LeapfrogMcmcSampledPosterior:
         check(self._lib.thy_lfm_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def setPool(self, x) -> None:
+        """Replace the pool (P, d): warm start near the mode or resume from ``pool()``."""
+        x = np.ascontiguousarray(_arr(x).reshape(self.config.samplePoolSize, self.posterior.domainDimension))
+        check(self._lib.thy_lfm_set_pool(self._h, _ptr(x)))
+
     def pool(self):
         P = self.config.samplePoolSize
         x = np.empty((P, self.posterior.domainDimension))
@@ -296,6 +302,7 @@ register("thy_slq_live_points", C.c_int, [_vp, _i64p, _dp, _dp])
 register("thy_slq_retired_log_x", C.c_int, [_vp, C.c_int, C.c_int64, _dp, _i64p])
 SLQ_INTEGRAND = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 register("thy_slq_integrate", C.c_int, [_vp, SLQ_INTEGRAND, C.c_void_p, C.c_double, _dp, _dp, _dp])
+register("thy_slq_load_balance", C.c_int, [_vp, _dp, _dp])
 register("thy_slq_set_trace", C.c_int, [_vp, C.c_int])
 register("thy_slq_phase_times", C.c_int, [_vp, _dp, _i64p])
 SLQ_PHASES = ("all_gather_keys", "radix_select_flags_values", "walk_adapt", "wait_quadrature", "round_control",
@@ -434,6 +441,12 @@ class SlqIntegratedPosterior:
         stat, integ = C.c_double(), C.c_double()
         check(self._lib.thy_slq_integrate(self._h, cb, None, float(logShift), C.byref(stat), C.byref(integ), None))
         return stat.value if reference else integ.value
+
+    def loadBalance(self):
+        """(mean, max) number of points this rank replaced per round."""
+        a, b = C.c_double(), C.c_double()
+        check(self._lib.thy_slq_load_balance(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def setTrace(self, enable: bool) -> None:
         check(self._lib.thy_slq_set_trace(self._h, 1 if enable else 0))

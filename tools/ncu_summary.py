@@ -67,7 +67,11 @@ def main():
                     rec[RAW_KEYS[h] + "_bytes"] = to_bytes(v, units[i])
                 else:
                     try:
-                        rec[RAW_KEYS[h]] = float(v.replace(",", ""))
+                        x = float(v.replace(",", ""))
+                        if RAW_KEYS[h] == "duration_us":   # ncu picks the unit per report
+                            x *= {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3,
+                                  "second": 1e6, "s": 1e6}.get(units[i], 1.0)
+                        rec[RAW_KEYS[h]] = x
                     except ValueError:
                         rec[RAW_KEYS[h]] = v
         launches.append(rec)

@@ -82,6 +82,11 @@ def main():
                                        [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.2), "theta")])
         cfg = t.LeapfrogMcmcConfig(stepsBetweenSamples=10, warmupStepCount=1, samplePoolSize=pool)
         lfm = t.LeapfrogMcmcSampledPosterior.of(cfg, "euclidean", post, rngSeed=3 + rank)   # one independent sub-pool per rank
+        # The pool `.of` draws from the sigma = 10 prior sits ~10^5 posterior widths from the mode in 1000 dimensions: no
+        # proposal is ever accepted there (round 1 reported acceptance 0.0).  Start it in the typical set instead, as a user
+        # would after an optimiser: theta* + posterior-width noise (sd ~ sigma sqrt(d/n) = 0.01).
+        lfm.setPool(theta[None, :] + 0.01 * np.random.default_rng(100 + rank).standard_normal((pool, d)))
+        lfm.runSweeps(1)
         barrier()
         t0 = time.perf_counter()
         lfm.runSweeps(args.c3_sweeps)
