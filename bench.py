@@ -280,6 +280,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    if args.only_slq:
+        def _barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        out = run_slq_leg(t, torch, dist, rank, world, torch.cuda.current_stream(), _barrier)
+        if rank == 0:
+            print(json.dumps({"slq": out}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     prob = synthetic_problem()
     post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", prob["pm"], prob["pci"])],
                                    [t.GaussianLinearLikelihood.of(prob["A"], prob["y"], prob["ci"], "theta")])
@@ -559,6 +572,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-slq", action="store_true")
+    ap.add_argument("--only-slq", action="store_true", help="run just the SLQ leg and print its dict (diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

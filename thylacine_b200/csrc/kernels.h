@@ -63,7 +63,12 @@ bool slq_walk_supported(const thy_model_s* m);
 // c_max sizes the grid; the walker count and the round number are read from device words (graph replay)
 thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long long Pl, int M, uint64_t seed,
                            const long long* round_dev, int rank, const int* sidx, const unsigned char* flags, double* x,
-                           double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s);
+                           double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s,
+                           const float* zpre = nullptr, const double* lacc = nullptr, int pre_groups = 0);
+// the round's proposal normals / acceptance thresholds for walker groups [0, groups), drawn ahead of the walk
+size_t slq_walk_rng_floats_per_group(const thy_model_s* m, int M);
+thy_status launch_slq_walk_rng(thy_model_s* m, int groups, int M, uint64_t seed, const long long* round_dev, int rank,
+                               float* zpre, double* lacc, cudaStream_t s);
 
 // link functions (device), shared by the generic and FD kernels
 __device__ __forceinline__ double link_eval(int link, double z) {

@@ -49,6 +49,9 @@ struct thy_slq_s {
   thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers of the per-step path
   thy::DevBuf<int> slot, accepted;
   thy::DevBuf<double> sigma, sig_part;                   // per-dimension spread of the live pool
+  thy::DevBuf<float> zpre;                               // pre-drawn walk normals (sharded pools: few walkers per rank)
+  thy::DevBuf<double> lacc;                              // pre-drawn acceptance thresholds
+  int pre_groups = 0;                                    // walker groups covered by zpre / lacc (0: drawn in the walk)
   thy::DevBuf<double> scalars;                           // [0] walk scale, [1] threshold, [4] last rate, [5] accepted, [6] proposed
   // quadrature (slq_evidence.cu)
   thy::DevBuf<double> ev_lt, ev_segsum, ev_part, abs_state, abs_out;
@@ -78,6 +81,7 @@ struct thy_slq_s {
   double tsum[7] = {0, 0, 0, 0, 0, 0, 0};
   long long tcount = 0;
   bool finished = false;
+  double host_wait_s = 0.0, host_enqueue_s = 0.0;   // THY_SLQ_TIMING: host seconds waiting for round r-2 / enqueuing rounds
   thy_slq_stats stats{};
   ~thy_slq_s() {
     if (graph) cudaGraphExecDestroy(graph);
@@ -398,6 +402,9 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, h->side2>>>(nrows, d, h->sig_part.ptr, nslab, h->sigma.ptr);
   count_launch(2);
   if (tracing) cudaEventRecord(h->tev[7], h->side2);
+  // the walk's randomness for this round, drawn while the main stream gathers and selects (sharded pools only)
+  if (h->fused_walk && h->pre_groups > 0)
+    THY_TRY(launch_slq_walk_rng(m, h->pre_groups, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->zpre.ptr, h->lacc.ptr, h->side2));
   THY_CUDA_CHECK(cudaEventRecord(h->ev_sigma, h->side2));
   // ---- every rank sees every log-likelihood: ONE collective per round ----
   const double* keys = h->ll.ptr;
@@ -432,7 +439,8 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sigma, 0));
   if (h->fused_walk) {
     THY_TRY(launch_slq_walk(m, Kr, h->count_dev.ptr, h->Pl, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->sidx.ptr, h->flags.ptr,
-                            h->x.ptr, h->ll.ptr, h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s));
+                            h->x.ptr, h->ll.ptr, h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s,
+                            h->pre_groups > 0 ? h->zpre.ptr : nullptr, h->lacc.ptr, h->pre_groups));
   } else {
     int c = Kr;   // single GPU: every retiree is local
     if (h->world > 1) {
@@ -542,6 +550,7 @@ static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* conve
       *converged = true;
       break;
     }
+    const auto hw0 = std::chrono::steady_clock::now();
     if (h->rounds >= 2) {
       THY_CUDA_CHECK(cudaEventSynchronize(h->ev_round[(h->rounds - 2) % 3]));
       const long long fc = *(volatile long long*)h->host_conv;
@@ -550,7 +559,10 @@ static thy_status slq_live_phase(thy_slq_s* h, long long max_rounds, bool* conve
         break;
       }
     }
+    const auto hw1 = std::chrono::steady_clock::now();
     THY_TRY(slq_round(h, (int)std::min<long long>(h->K, remaining)));
+    h->host_wait_s += std::chrono::duration<double>(hw1 - hw0).count();
+    h->host_enqueue_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - hw1).count();
   }
   return THY_OK;
 }
@@ -663,6 +675,16 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     if (!ok) st = fail(THY_ERR_CUDA, "SLQ stream / event setup failed");
     else *h->host_conv = -1;
     h->fused_walk = !cfg->disableFusedWalk && slq_walk_supported(m);
+    // Sharded pool: a rank replaces ~K / world points per round and its walk is latency-bound, so the walk's randomness is
+    // drawn ahead on a side stream for 1.25 K / world + 64 walkers (the rest, if a rank ever has more, draw in place).
+    const char* pre_env = std::getenv("THY_SLQ_PREDRAW");   // 0 / 1 force off / on (measurement knob)
+    const bool predraw = pre_env ? pre_env[0] == '1' : world > 1;
+    if (h->fused_walk && predraw && st == THY_OK) {
+      const long long walkers = std::min<long long>(K, (5LL * K) / (4LL * world) + 64);
+      h->pre_groups = (int)((walkers + 7) / 8);
+      chk(h->zpre.reserve((size_t)h->pre_groups * slq_walk_rng_floats_per_group(m, h->M)));
+      chk(h->lacc.reserve((size_t)h->pre_groups * h->M * 8));
+    }
     const char* ng = std::getenv("THY_SLQ_GRAPH");
     h->use_graph = !(ng && ng[0] == '0');
     const char* tr = std::getenv("THY_SLQ_TRACE");
@@ -695,6 +717,9 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     chk(h->abs_state.upload(stt, s));
     std::vector<long long> ctl = {0, 0, -1};
     chk(h->ctl.upload(ctl, s));
+    // First collective on the communicator here, not inside the first round: NCCL sets its channels up lazily at the
+    // first call (hundreds of milliseconds), which would otherwise be charged to the simulation.
+    if (st == THY_OK && world > 1) chk(comm_all_gather_f64(comm, h->ll.ptr, h->keys_all.ptr, (size_t)Pl, s));
     if (cudaStreamSynchronize(s) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
   }
   if (st != THY_OK) {
@@ -706,6 +731,9 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
 }
 
 thy_status thy_slq_destroy(thy_slq_t h) {
+  if (h && std::getenv("THY_SLQ_TIMING") && h->rounds > 0)
+    std::fprintf(stderr, "[thy slq timing] rank %d at destroy: %lld rounds, graph %s; host: %.3f s waiting for round r-2, %.3f s "
+                 "enqueuing\n", h->rank, h->rounds, h->graph ? "on" : "off", h->host_wait_s, h->host_enqueue_s);
   thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (h && h->trace && h->tcount > 0 && std::getenv("THY_SLQ_TRACE")) {
     std::fprintf(stderr, "[thy slq trace] rank %d: %lld rounds; us/round:", h->rank, h->tcount);
@@ -766,8 +794,11 @@ thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   cudaStream_t s = h->model->stream;
   std::vector<double> ao((size_t)h->A * 2);
   bool conv = false;
+  const bool timing = std::getenv("THY_SLQ_TIMING") != nullptr;   // host wall-clock split of the run on stderr
+  const auto t_live0 = std::chrono::steady_clock::now();
   THY_TRY(slq_live_phase(h, (long long)1 << 60, &conv));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  const auto t_live1 = std::chrono::steady_clock::now();
   // drainSamplePool (SlqEngine.scala:171-180): the remaining live points in ascending order
   const double* keys = h->ll.ptr;
   if (h->world > 1) {
@@ -814,6 +845,11 @@ thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   h->stats.walk_scale = sc[0];
   h->stats.walk_acceptance = sc[6] > 0 ? sc[5] / sc[6] : 0.0;
   h->stats.likelihood_evaluations = h->evals;
+  if (timing)
+    std::fprintf(stderr, "[thy slq timing] rank %d: live phase %.3f s (%lld rounds, graph %s; host: %.3f s waiting for round r-2, "
+                 "%.3f s enqueuing), drain + statistics %.3f s\n", h->rank,
+                 std::chrono::duration<double>(t_live1 - t_live0).count(), h->rounds, h->graph ? "on" : "off", h->host_wait_s,
+                 h->host_enqueue_s, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_live1).count());
   h->finished = true;
   if (out_stats) *out_stats = h->stats;
   return THY_OK;

@@ -41,7 +41,43 @@ struct WalkParams {
   const double* sigma;   // [d]
   const double* scalars; // [0] walk scale, [1] threshold
   int* accepted;         // [c] per-walker acceptance tally (+=)
+  // pre-drawn randomness of this round for walker groups [0, pre_groups) (k_slq_walk_rng), or null: drawn in place
+  const float* zpre;     // [group][M][KS][32] proposal normals in the walk kernel's lane order
+  const double* lacc;    // [group][M][8] ln(1 - u) of the Metropolis test
+  int pre_groups;
 };
+
+// The walk's random numbers do not depend on its state.  With live points sharded over several GPUs a rank has few walkers
+// (7 812 of 62 500 at 8 ranks), a warp runs alone on its scheduler, and the 40 sequential steps of a walker were mostly
+// Philox rounds and Box-Muller evaluated one dependent instruction at a time (profiles/r02_ncu_walk_low_occupancy.json:
+// ~1600 instructions per step, `wait` 41 %).  k_slq_walk_rng draws all of a round's normals and acceptance thresholds for
+// all (group, step) pairs at once -- one warp per pair, on the pool-spread stream, while the all-gather and the selection
+// occupy the main stream -- in exactly the order and precision the in-place path uses (same Philox calls, same fp32
+// Box-Muller), so both paths produce the same walk.
+template <int NT>
+__global__ void __launch_bounds__(256) k_slq_walk_rng(int groups, int M, uint64_t seed, const long long* __restrict__ round_dev,
+                                                      int rank, float* __restrict__ zpre, double* __restrict__ lacc) {
+  constexpr int KS = 2 * NT;
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)groups * M) return;
+  const int grp = (int)(wid / M), step = (int)(wid % M);
+  const int g8 = lane >> 2, q4 = lane & 3;
+  const uint64_t key = ((uint64_t)rank << 40) | (uint64_t)(grp * 8 + g8);
+  const uint64_t gstep = (uint64_t)*round_dev * (uint64_t)M + (uint64_t)step;
+  float* zrow = zpre + ((size_t)wid * KS) * 32 + lane;
+#pragma unroll
+  for (int kk = 0; kk < KS; kk += 2) {
+    double z0, z1;
+    rng_normal_pair_fast(seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z0, z1);
+    zrow[(size_t)kk * 32] = (float)z0;         // z0, z1 are fp32 values widened to double: the round trip is exact
+    zrow[(size_t)(kk + 1) * 32] = (float)z1;
+  }
+  if (q4 == 0) {
+    const RngDraw u = rng_uniform2(seed, key, 0, RNG_SLQ_ACCEPT, gstep);
+    lacc[(size_t)wid * 8 + g8] = log(1.0 - u.u0);
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
@@ -107,15 +143,28 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
     double pcur = live ? p.lpr[src] : 0.0;
     int acc = 0;
 
+    const bool pre = p.zpre != nullptr && grp < p.pre_groups;
     for (int step = 0; step < p.M; ++step) {
       const uint64_t gstep = round * (uint64_t)p.M + (uint64_t)step;
+      const float* zrow = pre ? p.zpre + (((size_t)grp * p.M + step) * KS) * 32 + lane : nullptr;
+      float zf[KS];
+      if (pre) {
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) zf[kk] = __ldg(zrow + (size_t)kk * 32);
+      }
+      const double lthr = pre ? p.lacc[((size_t)grp * p.M + step) * 8 + g8] : 0.0;
       // ---- propose + prior of the proposal ----
       double pacc = 0.0;
       bool inside = true;
 #pragma unroll
       for (int kk = 0; kk < KS; kk += 2) {
         double z0, z1;
-        rng_normal_pair_fast(p.seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z0, z1);
+        if (pre) {
+          z0 = (double)zf[kk];
+          z1 = (double)zf[kk + 1];
+        } else {
+          rng_normal_pair_fast(p.seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z0, z1);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int k = 4 * (kk + h) + q4;
@@ -165,8 +214,12 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
       const double lnew = (p.distribution == THY_DIST_GAUSSIAN) ? (-0.5 * q + p.log_const)
                                                                 : (p.log_const - (1.0 + p.n) / 2.0 * log(1.0 + q));
       // ---- Metropolis test w.r.t. the prior, hard likelihood constraint (same draw as k_slq_accept) ----
-      const RngDraw u = rng_uniform2(p.seed, key, 0, RNG_SLQ_ACCEPT, gstep);
-      const bool ok = live && isfinite(lpn) && isfinite(lnew) && (lnew > thr) && (lpn - pcur >= log(1.0 - u.u0));
+      double lu = lthr;
+      if (!pre) {
+        const RngDraw u = rng_uniform2(p.seed, key, 0, RNG_SLQ_ACCEPT, gstep);
+        lu = log(1.0 - u.u0);
+      }
+      const bool ok = live && isfinite(lpn) && isfinite(lnew) && (lnew > thr) && (lpn - pcur >= lu);
       if (ok) {
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) xf[kk] = xp[kk];
@@ -229,7 +282,8 @@ bool slq_walk_supported(const thy_model_s* m) {
 
 thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long long Pl, int M, uint64_t seed,
                            const long long* round_dev, int rank, const int* sidx, const unsigned char* flags, double* x,
-                           double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s) {
+                           double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s,
+                           const float* zpre, const double* lacc, int pre_groups) {
   if (c_max <= 0) return THY_OK;
   const LikDev& lk = m->lik_dev[0]->view;
   WalkParams p{};
@@ -249,6 +303,9 @@ thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long lon
   p.rank = rank;
   p.sidx = sidx;
   p.flags = flags;
+  p.zpre = zpre;
+  p.lacc = lacc;
+  p.pre_groups = zpre ? pre_groups : 0;
   p.x = x;
   p.ll = ll;
   p.lpr = lpr;
@@ -264,6 +321,29 @@ thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long lon
 #undef THY_WALK_CASE
     default: return fail(THY_ERR_UNSUPPORTED, "SLQ fused walk: unsupported width");
   }
+}
+
+// doubles / floats of pre-drawn randomness per walker group (8 walkers) for M steps
+size_t slq_walk_rng_floats_per_group(const thy_model_s* m, int M) {
+  const int nt = fused_nt_for(m->lik_dev[0]->view.dl);
+  return (size_t)M * 2 * nt * 32;
+}
+
+thy_status launch_slq_walk_rng(thy_model_s* m, int groups, int M, uint64_t seed, const long long* round_dev, int rank,
+                               float* zpre, double* lacc, cudaStream_t s) {
+  if (groups <= 0) return THY_OK;
+  const int nt = fused_nt_for(m->lik_dev[0]->view.dl);
+  const unsigned grid = (unsigned)(((long long)groups * M + 7) / 8);
+  switch (nt) {
+#define THY_RNG_CASE(N) case N: k_slq_walk_rng<N><<<grid, 256, 0, s>>>(groups, M, seed, round_dev, rank, zpre, lacc); break;
+    THY_RNG_CASE(1) THY_RNG_CASE(2) THY_RNG_CASE(3) THY_RNG_CASE(4) THY_RNG_CASE(5) THY_RNG_CASE(7)
+    THY_RNG_CASE(10) THY_RNG_CASE(13) THY_RNG_CASE(16)
+#undef THY_RNG_CASE
+    default: return fail(THY_ERR_UNSUPPORTED, "SLQ fused walk: unsupported width");
+  }
+  count_launch();
+  THY_CUDA_CHECK(cudaGetLastError());
+  return THY_OK;
 }
 
 }  // namespace thy

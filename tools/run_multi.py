@@ -82,9 +82,12 @@ def main():
                                        [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.2), "theta")])
         cfg = t.LeapfrogMcmcConfig(stepsBetweenSamples=10, warmupStepCount=1, samplePoolSize=pool)
         lfm = t.LeapfrogMcmcSampledPosterior.of(cfg, "euclidean", post, rngSeed=3 + rank)   # one independent sub-pool per rank
-        # The pool `.of` draws from the sigma = 10 prior sits ~10^5 posterior widths from the mode in 1000 dimensions: no
-        # proposal is ever accepted there (round 1 reported acceptance 0.0).  Start it in the typical set instead, as a user
-        # would after an optimiser: theta* + posterior-width noise (sd ~ sigma sqrt(d/n) = 0.01).
+        # Start the pool in the typical set (theta* + posterior-width noise, sd ~ sigma sqrt(d/n) = 0.01), as a user would
+        # after an optimiser, instead of the sigma = 10 prior.  The acceptance still reads 0.0 at d = 1000, and that is the
+        # reference's algorithm, not this implementation: the proposal reflects x_i through a partner, x' = 2 x_j - x_i
+        # (LeapfrogMcmcEngine.scala:104-121), so for a pool distributed like the target x' - mu = 2 e_j - e_i has FIVE times
+        # the target's variance and log p(x') - log p(x_i) ~ -2 d = -2000.  (tests/test_lfm_gpu.py: ~8 % acceptance at d = 3.)
+        # The figure below is therefore proposal evaluations per second.
         lfm.setPool(theta[None, :] + 0.01 * np.random.default_rng(100 + rank).standard_normal((pool, d)))
         lfm.runSweeps(1)
         barrier()
