@@ -258,6 +258,12 @@ def run_slq_leg(t, torch, dist, rank, world, stream, barrier):
     ph = slq.phaseTimes()
     slq.setTrace(False)
     out["phase_us_per_round"] = {k: (max_over_ranks(v) if k != "rounds" else v) for k, v in ph.items()}
+    mode = int(ph.get("graph_replay_bit0_peer_memory_bit1", 0))
+    out["round_replayed_from_cuda_graph"] = bool(mode & 1)
+    if world > 1:
+        out["collective"] = ("none per round: new log-likelihoods are written into every rank's memory over NVLink peer memory by "
+                             "the walk kernel (slq_p2p.cu); NCCL on the product communicator (thy_comm_create) for set-up and "
+                             "the final drain" if (mode & 2) else out["collective"])
     slq.close()
     post.close()
     if comm is not None:

@@ -340,6 +340,7 @@ typedef struct thy_slq_stats {
 /* seeds: host [n_seeds * d] points placed in the first pool slots of rank 0 (SlqEngine.scala:384-389,409), or NULL. */
 thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng_seed, const double* seeds, int n_seeds,
                           thy_comm_t comm, thy_slq_t* out);
+/* Collective when the handle was built on a communicator with more than one rank (every rank destroys its handle). */
 thy_status thy_slq_destroy(thy_slq_t h);
 /* rebuildSampleSimulation (SlqIntegratedPosterior.scala:76-80): run to convergence / maxIterationCount, drain. */
 thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats);
@@ -367,8 +368,9 @@ thy_status thy_slq_integrate(thy_slq_t h, thy_slq_integrand integrand, void* use
 /* Phase trace: while enabled, rounds run as plain launches with CUDA events between the phases.  out_us[0..4] are the
  * consecutive phases of a round on the main stream (all-gather of the ranks' keys; radix select + flags + retired
  * values; walk + adapt; wait for the quadrature stream; round control), mean microseconds per traced round; out_us[5] the
- * pool-spread kernels, which run on a side stream beside phases 0-1; out_us[6] = 1 when untraced full rounds replay from
- * a CUDA graph, else 0. */
+ * pool-spread kernels, which run on a side stream beside phases 0-1; out_us[6]: bit 0 = untraced full rounds replay from
+ * a CUDA graph, bit 1 = new keys travel over NVLink peer memory instead of an NCCL all-gather (phase 0 is then the wait
+ * for the peers' flags + the local apply). */
 /* Load balance of the sharded live pool: mean and largest number of points THIS rank had to replace in one round (the
  * K globally lowest points are wherever they are; a round lasts as long as its busiest rank's walk). */
 thy_status thy_slq_load_balance(thy_slq_t h, double* out_mean_local, double* out_max_local);

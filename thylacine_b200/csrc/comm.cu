@@ -3,8 +3,11 @@
 // The reference has no collectives at all (single JVM process).
 #include "comm.h"
 #include <dlfcn.h>
+#include <unistd.h>
 #include <cstring>
 #include <vector>
+#include <mutex>
+#include <set>
 
 namespace thy {
 
@@ -45,10 +48,22 @@ NcclApi& api() {
   return a;
 }
 
+std::mutex g_live_mutex;
+std::set<const thy_comm_s*> g_live_comms;   // handles between create and destroy (engines check before a late collective)
+
 thy_status nccl_fail(ncclResult_t r, const char* what) {
   return fail(THY_ERR_NCCL, std::string(what) + ": " + (api().GetErrorString ? api().GetErrorString(r) : "nccl error"));
 }
 }  // namespace
+
+bool comm_is_live(const thy_comm_s* c) {
+  std::lock_guard<std::mutex> lock(g_live_mutex);
+  return c && g_live_comms.count(c) != 0;
+}
+static void comm_register(const thy_comm_s* c, bool live) {
+  std::lock_guard<std::mutex> lock(g_live_mutex);
+  if (live) g_live_comms.insert(c); else g_live_comms.erase(c);
+}
 
 thy_status comm_all_gather_f64(thy_comm_s* c, const double* send, double* recv, size_t count, cudaStream_t s) {
   if (!c || c->world == 1) {
@@ -69,6 +84,86 @@ thy_status comm_all_reduce_i64(thy_comm_s* c, long long* buf, size_t count, int 
   if (!c || c->world == 1) return THY_OK;
   ncclResult_t r = api().AllReduce(buf, buf, count, kNcclInt64, op, c->nccl_comm, s);
   return r == 0 ? THY_OK : nccl_fail(r, "ncclAllReduce");
+}
+
+// ---- peer mapping (NVLink peer memory for the product's own exchange kernels) ----------------------------------------
+namespace {
+struct PeerRecord {             // 96 bytes = 12 doubles, exchanged with one NCCL all-gather
+  long long pid;
+  long long device;
+  unsigned long long ptr;
+  cudaIpcMemHandle_t handle;    // 64 bytes
+  long long pad;
+};
+static_assert(sizeof(PeerRecord) == 96, "PeerRecord layout");
+}  // namespace
+
+thy_status comm_map_peers(thy_comm_s* c, void* local, std::vector<void*>& out_ptrs, std::vector<void*>& opened, bool* ok,
+                          cudaStream_t s) {
+  *ok = false;
+  if (!c || c->world <= 1) {
+    out_ptrs.assign(1, local);
+    *ok = true;
+    return THY_OK;
+  }
+  const int world = c->world, rank = c->rank;
+  int dev = 0;
+  THY_CUDA_CHECK(cudaGetDevice(&dev));
+  PeerRecord mine{};
+  mine.pid = (long long)getpid();
+  mine.device = dev;
+  mine.ptr = (unsigned long long)local;
+  bool good = cudaIpcGetMemHandle(&mine.handle, local) == cudaSuccess;
+  if (!good) cudaGetLastError();
+  DevBuf<double> box;
+  THY_TRY(box.reserve((size_t)world * 12));
+  THY_CUDA_CHECK(cudaMemcpyAsync(box.ptr + (size_t)rank * 12, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+  THY_TRY(comm_all_gather_f64(c, box.ptr + (size_t)rank * 12, box.ptr, 12, s));
+  std::vector<PeerRecord> all(world);
+  THY_CUDA_CHECK(cudaMemcpyAsync(all.data(), box.ptr, (size_t)world * sizeof(PeerRecord), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  out_ptrs.assign(world, nullptr);
+  for (int r = 0; r < world && good; ++r) {
+    if (r == rank) {
+      out_ptrs[r] = local;
+    } else if (all[r].pid == mine.pid) {   // another thread of this process: plain peer access
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, dev, (int)all[r].device) != cudaSuccess || !can) {
+        good = false;
+        break;
+      }
+      const cudaError_t e = cudaDeviceEnablePeerAccess((int)all[r].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) good = false;
+      cudaGetLastError();
+      out_ptrs[r] = (void*)all[r].ptr;
+    } else {
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        good = false;
+        break;
+      }
+      out_ptrs[r] = p;
+      opened.push_back(p);
+    }
+  }
+  // the verdict must be the same everywhere: min over ranks
+  DevBuf<long long> flag;
+  THY_TRY(flag.reserve(1));
+  const long long mineok = good ? 1 : 0;
+  THY_CUDA_CHECK(cudaMemcpyAsync(flag.ptr, &mineok, sizeof(long long), cudaMemcpyHostToDevice, s));
+  THY_TRY(comm_all_reduce_i64(c, flag.ptr, 1, 3 /* min */, s));
+  long long allok = 0;
+  THY_CUDA_CHECK(cudaMemcpyAsync(&allok, flag.ptr, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (!allok) {
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
+    opened.clear();
+    out_ptrs.clear();
+    cudaGetLastError();
+  }
+  *ok = allok != 0;
+  return THY_OK;
 }
 
 }  // namespace thy
@@ -117,6 +212,7 @@ thy_status thy_comm_create(int rank, int world, const unsigned char unique_id[12
     }
     c->nccl_comm = nc;
   }
+  comm_register(c, true);
   *out = c;
   return THY_OK;
 }
@@ -146,6 +242,7 @@ thy_status thy_comm_create_all(int n_devices, const int* devices, thy_comm_t* ou
     c->rank = i;
     c->world = n_devices;
     c->nccl_comm = comms[i];
+    comm_register(c, true);
     out[i] = c;
   }
   return THY_OK;
@@ -169,6 +266,7 @@ thy_status thy_set_device(int device) {
 }
 
 thy_status thy_comm_destroy(thy_comm_t c) {
+  if (c) comm_register(c, false);
   if (c && c->nccl_comm && api().ok) api().CommDestroy((ncclComm_t)c->nccl_comm);
   delete c;
   return THY_OK;

@@ -52,6 +52,12 @@ struct thy_slq_s {
   thy::DevBuf<float> zpre;                               // pre-drawn walk normals (sharded pools: few walkers per rank)
   thy::DevBuf<double> lacc;                              // pre-drawn acceptance thresholds
   int pre_groups = 0;                                    // walker groups covered by zpre / lacc (0: drawn in the walk)
+  // NVLink peer-memory exchange of new keys (slq_p2p.cu); off => one NCCL all-gather of all keys per round
+  bool p2p = false;
+  thy::DevBuf<unsigned char> p2p_buf;
+  thy::DevBuf<unsigned long long> p2p_bases;
+  std::vector<void*> p2p_opened;
+  thy::P2pView p2p_view{};
   thy::DevBuf<double> scalars;                           // [0] walk scale, [1] threshold, [4] last rate, [5] accepted, [6] proposed
   // quadrature (slq_evidence.cu)
   thy::DevBuf<double> ev_lt, ev_segsum, ev_part, abs_state, abs_out;
@@ -96,6 +102,7 @@ struct thy_slq_s {
     if (host_ao) cudaFreeHost(host_ao);
     if (host_c) cudaFreeHost(host_c);
     if (host_conv) cudaFreeHost(host_conv);
+    for (void* q : p2p_opened) cudaIpcCloseMemHandle(q);
   }
 };
 
@@ -409,7 +416,13 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   // ---- every rank sees every log-likelihood: ONE collective per round ----
   const double* keys = h->ll.ptr;
   if (h->world > 1) {
-    THY_TRY(comm_all_gather_f64(h->comm, h->ll.ptr, h->keys_all.ptr, (size_t)h->Pl, s));
+    if (h->p2p) {
+      // no collective: the peers' walks staged their new keys in this rank's memory over NVLink; wait for their flags
+      // and fold the pairs into the local copy of all keys
+      THY_TRY(slq_p2p_wait_and_apply(h->p2p_view, h->p2p_buf.ptr, h->ctl.ptr, h->scalars.ptr, h->keys_all.ptr, s));
+    } else {
+      THY_TRY(comm_all_gather_f64(h->comm, h->ll.ptr, h->keys_all.ptr, (size_t)h->Pl, s));
+    }
     keys = h->keys_all.ptr;
   }
   mark(1);
@@ -471,6 +484,8 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability,
                                  h->count_dev.ptr, h->M, h->accepted.ptr);
   count_launch();
+  // this rank's new keys go to every rank's staging area over NVLink; then the flag says so
+  if (h->p2p) THY_TRY(slq_p2p_signal(h->p2p_view, h->Pl, h->sidx.ptr, h->ll.ptr, h->count_dev.ptr, h->ctl.ptr, s));
   mark(3);
   THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join, 0));
   mark(4);
@@ -720,6 +735,28 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     // First collective on the communicator here, not inside the first round: NCCL sets its channels up lazily at the
     // first call (hundreds of milliseconds), which would otherwise be charged to the simulation.
     if (st == THY_OK && world > 1) chk(comm_all_gather_f64(comm, h->ll.ptr, h->keys_all.ptr, (size_t)Pl, s));
+    // Peer-memory exchange (THY_SLQ_P2P=0 keeps the NCCL all-gather): every rank maps every rank's
+    // exchange buffer.  The verdict is collective, so either all ranks use it or none does.
+    const char* p2p_env = std::getenv("THY_SLQ_P2P");
+    if (st == THY_OK && world > 1 && !(p2p_env && p2p_env[0] == '0')) {
+      const long long cap = K;
+      chk(h->p2p_buf.reserve(p2p_bytes(world, cap)));
+      if (st == THY_OK && cudaMemsetAsync(h->p2p_buf.ptr, 0, p2p_bytes(world, cap), s) != cudaSuccess) st = fail(THY_ERR_CUDA, "memset");
+      if (st == THY_OK && cudaStreamSynchronize(s) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
+      std::vector<void*> ptrs;
+      bool ok = false;
+      if (st == THY_OK) chk(comm_map_peers(comm, h->p2p_buf.ptr, ptrs, h->p2p_opened, &ok, s));
+      if (st == THY_OK && ok) {
+        std::vector<unsigned long long> bases(world);
+        for (int r = 0; r < world; ++r) bases[r] = (unsigned long long)ptrs[r];
+        chk(h->p2p_bases.upload(bases, s));
+        h->p2p_view.peer_base = h->p2p_bases.ptr;
+        h->p2p_view.world = world;
+        h->p2p_view.rank = h->rank;
+        h->p2p_view.cap = cap;
+        h->p2p = st == THY_OK;
+      }
+    }
     if (cudaStreamSynchronize(s) != cudaSuccess) st = fail(THY_ERR_CUDA, "SLQ initialisation failed");
   }
   if (st != THY_OK) {
@@ -731,6 +768,12 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
 }
 
 thy_status thy_slq_destroy(thy_slq_t h) {
+  if (h && h->p2p && h->world > 1 && comm_is_live(h->comm)) {
+    // peers hold mappings of this rank's exchange buffer and may still be writing into it: destroy is collective
+    cudaStreamSynchronize(h->model->stream);
+    comm_all_reduce_f64(h->comm, h->scalars.ptr + 3, 1, 0, h->model->stream);
+    cudaStreamSynchronize(h->model->stream);
+  }
   if (h && std::getenv("THY_SLQ_TIMING") && h->rounds > 0)
     std::fprintf(stderr, "[thy slq timing] rank %d at destroy: %lld rounds, graph %s; host: %.3f s waiting for round r-2, %.3f s "
                  "enqueuing\n", h->rank, h->rounds, h->graph ? "on" : "off", h->host_wait_s, h->host_enqueue_s);
@@ -758,7 +801,8 @@ thy_status thy_slq_phase_times(thy_slq_t h, double out_us[7], int64_t* out_round
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   for (int i = 0; i < 7; ++i)
     if (out_us) out_us[i] = h->tcount > 0 ? 1e3 * h->tsum[i] / h->tcount : 0.0;
-  if (out_us) out_us[6] = h->graph ? 1.0 : 0.0;   // 1 when untraced full rounds replay from a CUDA graph
+  // bit 0: untraced full rounds replay from a CUDA graph; bit 1: peer-memory exchange instead of the NCCL all-gather
+  if (out_us) out_us[6] = (h->graph ? 1.0 : 0.0) + (h->p2p ? 2.0 : 0.0);
   if (out_rounds) *out_rounds = h->tcount;
   return THY_OK;
 }
@@ -827,6 +871,7 @@ thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   double minl = 0.0;
   THY_CUDA_CHECK(cudaMemcpyAsync(&minl, h->ret_ll.ptr + h->live_iterations, sizeof(double), cudaMemcpyDeviceToHost, s));
   THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (sc[7] != 0.0) return fail(THY_ERR_STATE, "SLQ: a peer rank did not signal within 5 s (peer-memory exchange); results are invalid");
   double mean = 0.0, m2 = 0.0, hm = 0.0;
   for (int a = 0; a < h->A; ++a) {
     mean += ao[(size_t)a * 2];

@@ -53,6 +53,32 @@ __device__ __forceinline__ long long slq_pick_survivor(uint64_t seed, uint64_t k
 }
 #endif
 
+// ---- NVLink peer-memory exchange of the round's new keys (slq_p2p.cu) ----
+// Every rank owns one exchange buffer that all ranks map (CUDA IPC / peer access):
+//   pairs   [2 parities][world sources][cap] x 16 bytes  (global key index as int64 bits, new log-likelihood)
+//   counts  [2 parities][world sources] x int64           how many pairs a source staged
+//   flags   [world sources] x uint64                      last round whose walk that source has finished, + 1
+struct P2pView {
+  const unsigned long long* peer_base;   // device array [world]: rank r's exchange buffer as mapped on THIS rank (null: off)
+  int world, rank;
+  long long cap;
+};
+__host__ __device__ inline size_t p2p_pair_off(const P2pView& v, int parity, int src, long long w) {
+  return (((size_t)parity * v.world + src) * (size_t)v.cap + (size_t)w) * 16;
+}
+__host__ __device__ inline size_t p2p_count_off(const P2pView& v, int parity, int src) {
+  return (size_t)2 * v.world * (size_t)v.cap * 16 + ((size_t)parity * v.world + src) * 8;
+}
+__host__ __device__ inline size_t p2p_flag_off(const P2pView& v, int src) {
+  return (size_t)2 * v.world * (size_t)v.cap * 16 + (size_t)2 * v.world * 8 + (size_t)src * 8;
+}
+inline size_t p2p_bytes(int world, long long cap) { return (size_t)2 * world * (size_t)cap * 16 + (size_t)3 * world * 8; }
+thy_status slq_p2p_wait_and_apply(const P2pView& v, unsigned char* my_base, const long long* ctl, double* scalars,
+                                  double* keys_all, cudaStream_t s);
+// push this rank's new keys (sidx / ll after the walk) to every rank, then publish count and flag
+thy_status slq_p2p_signal(const P2pView& v, long long Pl, const int* sidx, const double* ll, const int* count_dev,
+                          const long long* ctl, cudaStream_t s);
+
 int slq_select_slices(long long Pl);
 thy_status slq_select_launch(const SelectBuffers& b, const double* keys, long long Pl, int world, int rank, int K,
                              double* vals, cudaStream_t s);

@@ -306,7 +306,7 @@ register("thy_slq_load_balance", C.c_int, [_vp, _dp, _dp])
 register("thy_slq_set_trace", C.c_int, [_vp, C.c_int])
 register("thy_slq_phase_times", C.c_int, [_vp, _dp, _i64p])
 SLQ_PHASES = ("all_gather_keys", "radix_select_flags_values", "walk_adapt", "wait_quadrature", "round_control",
-              "pool_spread_side_stream", "graph_replay")
+              "pool_spread_side_stream", "graph_replay_bit0_peer_memory_bit1")
 
 
 @dataclass
