@@ -523,13 +523,16 @@ def run_ours(args):
         peak, peak_src = load_fp64_peak()
         k_avg_ms = k_ms.value / max(k_n.value, 1)
         achieved = FLOPS_PER_EVAL * CHAINS / (k_avg_ms * 1e-3) / 1e12 if k_n.value else None
-        traffic = None
-        tp = ROOT / "profiles" / "ncu_fused_summary.json"
-        if tp.exists():
-            try:
-                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic = None   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        for tp, get in ((ROOT / "profiles" / "r02_ncu_fused_c2.json",
+                         lambda j: j["launches"][0]["dram_read_bytes"] + j["launches"][0]["dram_write_bytes"]),
+                        (ROOT / "profiles" / "ncu_fused_summary.json", lambda j: j.get("dram_bytes_per_launch"))):
+            if tp.exists():
+                try:
+                    traffic = get(json.loads(tp.read_text()))
+                    break
+                except Exception:
+                    traffic = None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = use_all_host_cores()
