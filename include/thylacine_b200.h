@@ -322,6 +322,13 @@ typedef struct thy_slq_config {
   int constrainedWalkSteps;           /* constrained-walk steps per replacement (default 20)                   */
   int keepRetiredPoints;              /* keep retired positions for thy_slq_sample (single GPU)                */
   int disableFusedWalk;               /* 1 = always use the per-step kernels (diagnostics; same random numbers) */
+  int referenceProposals;             /* 1 = the reference's own proposal mechanism and one-at-a-time pool update: the
+                                         cubical cover (PointInCubeCollection.scala:60-111, PointInCube.scala:84-117,
+                                         PointInInterval.scala:40-109, QuadratureDomainTelemetry.scala:27-110,
+                                         SlqEngine.scala:120-197,216-247,309-345).  Small pools, single GPU: geometry and
+                                         pool bookkeeping on the host, every logPdf on the device in batches of
+                                         sampleParallelism, quadrature on the device.  Ranks by the full posterior logPdf
+                                         as the reference does.  thy_slq_run only.                                  */
 } thy_slq_config;
 
 typedef struct thy_slq_stats {

@@ -95,13 +95,20 @@ def ready_for_sampling(points: np.ndarray):
 
 def cube_volumes(lower, upper) -> np.ndarray:
     """PointInCube.cubeVolume (:30-33): the SUM of the interval lengths (not the product) -- reproduced as written."""
-    return np.abs(upper - lower).sum(axis=1)
+    # summed left to right in Python floats (numpy's pairwise reduction would round differently from the device engine's loop)
+    out = np.empty(len(lower))
+    for i in range(len(lower)):
+        v = 0.0
+        for k in range(lower.shape[1]):
+            v += abs(float(upper[i, k]) - float(lower[i, k]))
+        out[i] = v
+    return out
 
 
 def choose_cube(volumes: np.ndarray, u: float) -> int:
     """MathOps.cdfStaircase over the volumes + the half-open lookup of PointInCubeCollection.getSample (:93-105)."""
-    cdf = np.cumsum(volumes) / volumes.sum()
-    return int(min(np.searchsorted(cdf, u, side="right"), len(volumes) - 1))
+    cdf = np.cumsum(volumes)                                   # sequential, like the device engine's loop
+    return int(min(np.searchsorted(cdf / cdf[-1], u, side="right"), len(volumes) - 1))
 
 
 # ---------------------------------------------------------------------------------------------- telemetry

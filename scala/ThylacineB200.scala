@@ -109,7 +109,7 @@ private[thylacine] object ThylacineB200 {
     I.withName("poolSize"), I.withName("abscissaNumber"), D.withName("domainScalingIncrement"),
     D.withName("targetAcceptanceProbability"), I.withName("sampleParallelism"), I.withName("maxIterationCount"),
     I.withName("minIterationCount"), I.withName("constrainedWalkSteps"), I.withName("keepRetiredPoints"),
-    I.withName("disableFusedWalk"))
+    I.withName("disableFusedWalk"), I.withName("referenceProposals"), MemoryLayout.paddingLayout(4))
   val slqStats: StructLayout = MemoryLayout.structLayout(                                 // SlqTelemetryUpdate.scala:20-29
     L.withName("iterations"), L.withName("total_retired"), L.withName("rounds"), L.withName("likelihood_evaluations"),
     D.withName("log_evidence_mean"), D.withName("log_evidence_std"), D.withName("neg_entropy_mean"), D.withName("min_logpdf"),

@@ -223,6 +223,48 @@ def test_slq_fused_walk_kernel_matches_the_per_step_kernels(case):
     assert np.max(np.abs(la[same] - lb[same]) / np.maximum(1.0, np.abs(lb[same]))) < 1e-12
 
 
+@pytest.mark.parametrize("batch", [1, 8])
+def test_slq_reference_proposals_replay_the_cubical_cover(batch):
+    """thy_slq_config.referenceProposals: the reference's own proposal mechanism (PointInCubeCollection.scala:60-111,
+    PointInCube.scala:84-117, PointInInterval.scala:40-109), one-at-a-time pool update (SlqEngine.scala:216-247) and
+    rebuild schedule (QuadratureDomainTelemetry.scala:48-49), replayed draw for draw by oracle/slq_cubical_cover.py with
+    the device engine's counter-based uniforms: same retirement sequence, same final pool, same number of proposals."""
+    from oracle import slq_cubical_cover as cc
+    rng = np.random.default_rng(4)
+    d, n, P = 3, 12, 40
+    A = rng.standard_normal((n, d))
+    y = A @ np.array([0.5, -0.3, 0.8]) + 0.3 * rng.standard_normal(n)
+    pri = [t.UniformPrior.fromBounds("theta", np.full(d, 4.0), np.full(d, -4.0))]
+    lik = [t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.6), "theta")]
+    post = t.UnnormalisedPosterior(pri, lik)
+    ref = o.Posterior([o.uniform_prior_from_bounds("theta", np.full(d, 4.0), np.full(d, -4.0))],
+                      [o.gaussian_linear_likelihood(A, y, np.full(n, 0.6), "theta")])
+    seed, max_it = 321, 700
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=3, domainScalingIncrement=0.1, targetAcceptanceProbability=0.3,
+                      sampleParallelism=batch, maxIterationCount=max_it, minIterationCount=max_it)
+    slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=seed, referenceProposals=True)
+    x0, _ = slq.livePoints()                                              # the prior draws the run starts from
+    slq.rebuildSampleSimulation()
+    got = slq.retiredLogLikelihoods()
+    live = int(slq.stats.iterations)
+    RNG_SLQ_REFERENCE = 12
+    uniform = lambda stream, k: ph.uniform2(seed, stream, 0, RNG_SLQ_REFERENCE, k)[0]
+    want, pool_x, pool_lp, nprop = cc.run_reference_slq(x0, ref.log_pdf, uniform,
+                                                        max_iterations=max_it, batch=batch)
+    assert live == want.size == max_it and got.size == live + P
+    assert np.max(np.abs(got[:live] - want) / np.maximum(1.0, np.abs(want))) < 1e-11
+    assert np.all(np.diff(got) >= 0) or np.all(np.diff(got[:live]) >= 0)
+    x1, lp1 = slq.livePoints()
+    assert np.array_equal(x1, pool_x) and np.max(np.abs(lp1 - pool_lp) / np.maximum(1.0, np.abs(pool_lp))) < 1e-11
+    assert int(slq.stats.rounds) == nprop                                 # proposals made (telemetry), rebuild discards included
+    lz, _ = slq.abscissaResults()
+    for a in range(3):                                                    # quadrature: one retirement per step
+        want_lz, _ = _replay_abscissa(got, P, 1, live, seed, a)
+        assert abs(lz[a] - want_lz) < 1e-9 * max(1.0, abs(want_lz))
+    slq.close()
+    post.close()
+
+
 def test_slq_duplicate_live_points_do_not_break_the_threshold_step():
     """A walker that never moves is an exact copy of a survivor (the reference nudges duplicates by one ulp,
     SlqEngine.scala:107-118); with one walk step per replacement most replacements are copies, so log-likelihood ties

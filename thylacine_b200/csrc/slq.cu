@@ -86,6 +86,7 @@ struct thy_slq_s {
   cudaEvent_t tev[8] = {};             // [0..5] phase boundaries on the main stream, [6], [7] around the pool spread
   double tsum[7] = {0, 0, 0, 0, 0, 0, 0};
   long long tcount = 0;
+  long long ref_rebuilds = 0;          // reference-faithful mode: cover rebuilds
   bool finished = false;
   double host_wait_s = 0.0, host_enqueue_s = 0.0;   // THY_SLQ_TIMING: host seconds waiting for round r-2 / enqueuing rounds
   thy_slq_stats stats{};
@@ -603,10 +604,246 @@ static thy_status slq_export_logx(thy_slq_s* h, int a, long long n, double* out_
   THY_CUDA_CHECK(cudaMemsetAsync(carry.ptr, 0, sizeof(double), s));
   for (long long i0 = 0; i0 < n; i0 += chunk) {
     const int cnt = (int)std::min<long long>(chunk, n - i0);
-    THY_TRY(slq_logx_launch(e, a, i0, cnt, h->P, h->K, live, h->seed, carry.ptr, buf.ptr, s));
+    // retirements per round of the prior-mass simulation: K in the default mode, 1 with the reference's proposals
+    THY_TRY(slq_logx_launch(e, a, i0, cnt, h->P, h->cfg.referenceProposals ? 1 : h->K, live, h->seed, carry.ptr, buf.ptr, s));
     THY_CUDA_CHECK(cudaMemcpyAsync(out_host + i0, buf.ptr, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
     THY_CUDA_CHECK(cudaStreamSynchronize(s));
   }
+  return THY_OK;
+}
+
+
+// ---- reference-faithful proposals (thy_slq_config.referenceProposals): the cubical cover -------------------------------
+// Reference: integration/slq/PointInInterval.scala:40-109, PointInCube.scala:30-117, PointInCubeCollection.scala:60-111,
+// QuadratureDomainTelemetry.scala:27-110 (rescaling disabled, its default), SlqEngine.scala:120-197,216-247,309-345.
+// The reference proposes ONE point at a time from a cover of the live pool by pairwise-disjoint, point-centred cubes
+// (cube chosen with probability proportional to the SUM of its side lengths, PointInCube.scala:30-33, sic), replaces the
+// pool minimum when the proposal's logPdf is above it, and rebuilds the cover from the pool after 1000 rejections in a row
+// (given at least one acceptance since the last rebuild).  The make-disjoint fold is a strictly sequential O(P^2) chain and
+// the pool update is one point at a time, so this mode is for SMALL pools: the geometry and the pool bookkeeping run on
+// the host in the library, every logPdf -- the hot path -- is evaluated on the device in batches of sampleParallelism
+// (the reference's fibres in flight: proposals of a batch come from the same cover, and what is left of a batch when the
+// cover is rebuilt is discarded), and the quadrature runs on the device as in the default mode, with one retirement per
+// step.  Ranking key = the full posterior logPdf, as in the reference (its measure quirk Q6 included).  Every random
+// number is a counter-based draw (stream, proposal index), so oracle/slq_cubical_cover.py replays the run draw for draw.
+namespace {
+
+struct CubicalCover {
+  int P = 0, d = 0;
+  std::vector<double> pt, lo, up, vol;   // [P][d] points / bounds; [P] "volumes"
+  void build() {
+    lo.assign((size_t)P * d, 0.0);
+    up.assign((size_t)P * d, 0.0);
+    // initialise (PointInCubeCollection.scala:60-85): half-width = largest distance to any other point, per dimension
+    for (int i = 0; i < P; ++i)
+      for (int k = 0; k < d; ++k) {
+        double h = 0.0;
+        for (int j = 0; j < P; ++j) {
+          const double a = std::fabs(pt[(size_t)j * d + k] - pt[(size_t)i * d + k]);
+          if (a > h) h = a;
+        }
+        lo[(size_t)i * d + k] = pt[(size_t)i * d + k] - h;
+        up[(size_t)i * d + k] = pt[(size_t)i * d + k] + h;
+      }
+    // makeDisjoint (PointInCube.scala:84-115): the fold, accumulator order included
+    std::vector<int> acc, work;
+    for (int c = 0; c < P; ++c) {
+      work.assign(1, c);
+      for (size_t a = 0; a < acc.size(); ++a) {
+        const int cur = acc[a], head = work[0];
+        bool inter = true;
+        for (int k = 0; k < d && inter; ++k) {
+          const double l1 = lo[(size_t)head * d + k], u1 = up[(size_t)head * d + k];
+          const double l2 = lo[(size_t)cur * d + k], u2 = up[(size_t)cur * d + k];
+          inter = ((u1 > l2) && (l1 < u2)) || ((u2 > l1) && (l2 < u1));
+        }
+        if (inter) {
+          int kbest = 0;
+          double best = -1.0;
+          for (int k = 0; k < d; ++k) {   // dimensionOfLargestSeparation: first maximum
+            const double df = pt[(size_t)head * d + k] - pt[(size_t)cur * d + k];
+            if (df * df > best) { best = df * df; kbest = k; }
+          }
+          const size_t ih = (size_t)head * d + kbest, ic = (size_t)cur * d + kbest;
+          const double p1 = pt[ih], p2 = pt[ic];
+          const bool one_larger = p1 > p2;
+          const double larger_lo = one_larger ? lo[ih] : lo[ic], smaller_up = one_larger ? up[ic] : up[ih];
+          const double avg = (p1 + p2) / 2.0;
+          double boundary;
+          if (larger_lo <= avg && smaller_up > avg) boundary = avg;
+          else if (larger_lo <= avg) boundary = smaller_up;
+          else boundary = larger_lo;   // (the reference throws when neither holds; unreachable for intersecting cubes)
+          if (one_larger) { lo[ih] = boundary; up[ic] = boundary; } else { up[ih] = boundary; lo[ic] = boundary; }
+        }
+        work.insert(work.begin() + 1, cur);   // Vector(new, current) ++ tail
+      }
+      acc = work;
+    }
+    // symmetrize (PointInInterval.scala:51-61) and volumes (PointInCube.scala:30-33: the SUM of the side lengths)
+    vol.assign(P, 0.0);
+    for (int i = 0; i < P; ++i) {
+      double v = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const size_t q = (size_t)i * d + k;
+        const double l1 = up[q] - pt[q], l2 = pt[q] - lo[q];
+        if (l1 > l2) up[q] = pt[q] + l2; else if (l1 < l2) lo[q] = pt[q] - l1;
+        v += std::fabs(up[q] - lo[q]);
+      }
+      vol[i] = v;
+    }
+  }
+  int choose(double u, std::vector<double>& cdf) const {   // MathOps.cdfStaircase + half-open lookup
+    cdf.resize(P);
+    double run = 0.0;
+    for (int i = 0; i < P; ++i) { run += vol[i]; cdf[i] = run; }
+    for (int i = 0; i < P; ++i)
+      if (cdf[i] / run > u) return i;
+    return P - 1;
+  }
+};
+
+constexpr uint32_t RNG_SLQ_REFERENCE = 12;
+inline double ref_uniform(uint64_t seed, int stream, long long n) {
+  return rng_uniform2(seed, (uint64_t)stream, 0, RNG_SLQ_REFERENCE, (uint64_t)n).u0;
+}
+
+}  // namespace
+
+static thy_status slq_run_reference(thy_slq_s* h) {
+  thy_model_s* m = h->model;
+  cudaStream_t s = m->stream;
+  const int P = (int)h->P, d = h->d, B = h->K;
+  const long long max_it = h->cfg.maxIterationCount;
+  const int rebuild_streak = 1000, exhausted_streak = 100000;   // QuadratureDomainTelemetry.scala:43,48-49
+  CubicalCover cov;
+  cov.P = P;
+  cov.d = d;
+  cov.pt.resize((size_t)P * d);
+  std::vector<double> key(P);
+  // ranking key = posterior logPdf of the pool (prior + likelihood), evaluated on the device
+  THY_TRY(eval_batch_dev(m, P, h->x.ptr, h->ll.ptr, nullptr, true));
+  THY_CUDA_CHECK(cudaMemcpyAsync(cov.pt.data(), h->x.ptr, (size_t)P * d * sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaMemcpyAsync(key.data(), h->ll.ptr, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  cov.build();
+  DevBuf<double> Xp, Lp;
+  THY_TRY(Xp.reserve((size_t)B * d));
+  THY_TRY(Lp.reserve((size_t)B));
+  std::vector<double> props((size_t)B * d), vals(B), cdf, retired, retired_x;
+  long long n = 0, processed = 0;
+  int acceptances_since_rebuild = 0, streak = 0;
+  long long acceptances = 0, rejections = 0, rebuilds = 0;
+  const EvidenceBuffers ev = ev_buffers(h);
+  const int chunk = (int)std::min<long long>(ev.stride, P);
+  bool converged = false;
+  // quadrature on the device, one retirement per step (K = 1): n_live = P throughout the live phase
+  auto flush_evidence = [&](long long upto) -> thy_status {
+    while (upto - processed >= chunk || (upto == (long long)retired.size() && upto > processed && converged)) {
+      const int cnt = (int)std::min<long long>(chunk, upto - processed);
+      if (cnt <= 0) break;
+      if (processed + cnt > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
+      THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + processed, retired.data() + processed, (size_t)cnt * sizeof(double),
+                                     cudaMemcpyHostToDevice, s));
+      THY_TRY(slq_evidence_launch(ev, h->A, cnt, h->P, 1, LLONG_MAX, processed, nullptr, h->seed, h->ret_ll.ptr + processed, 0, s));
+      THY_CUDA_CHECK(cudaMemcpyAsync(h->host_ao, h->abs_out.ptr, (size_t)h->A * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      THY_CUDA_CHECK(cudaStreamSynchronize(s));
+      processed += cnt;
+    }
+    return THY_OK;
+  };
+  while ((long long)retired.size() < max_it && streak < exhausted_streak && !converged) {
+    for (int b = 0; b < B; ++b) {
+      const int i = cov.choose(ref_uniform(h->seed, 0, n + b), cdf);
+      for (int k = 0; k < d; ++k) {
+        const size_t q = (size_t)i * d + k;
+        // PointInInterval.getSample (:76-77) at scale 1
+        props[(size_t)b * d + k] = (ref_uniform(h->seed, 1 + k, n + b) - 0.5) * 1.0 * (cov.up[q] - cov.lo[q]) + cov.pt[q];
+      }
+    }
+    THY_CUDA_CHECK(cudaMemcpyAsync(Xp.ptr, props.data(), (size_t)B * d * sizeof(double), cudaMemcpyHostToDevice, s));
+    THY_TRY(eval_batch_dev(m, B, Xp.ptr, Lp.ptr, nullptr, true));
+    THY_CUDA_CHECK(cudaMemcpyAsync(vals.data(), Lp.ptr, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    THY_CUDA_CHECK(cudaStreamSynchronize(s));
+    h->evals += B;
+    for (int b = 0; b < B; ++b) {
+      n += 1;
+      if ((long long)retired.size() >= max_it) break;
+      int imin = 0;
+      for (int j = 1; j < P; ++j)
+        if (key[j] < key[imin]) imin = j;
+      bool rebuilt = false;
+      if (key[imin] < vals[b]) {   // updateStateWithSampleCalculation (:216-233): strictly above the current minimum
+        retired.push_back(key[imin]);
+        if (h->cfg.keepRetiredPoints) retired_x.insert(retired_x.end(), cov.pt.begin() + (size_t)imin * d, cov.pt.begin() + (size_t)(imin + 1) * d);
+        std::copy(props.begin() + (size_t)b * d, props.begin() + (size_t)(b + 1) * d, cov.pt.begin() + (size_t)imin * d);
+        key[imin] = vals[b];
+        ++acceptances; ++acceptances_since_rebuild; streak = 0;
+      } else {
+        ++rejections; ++streak;
+      }
+      if (streak >= rebuild_streak && acceptances_since_rebuild >= 1) {   // initiateRebuild -> rebuildDomain (:309-345)
+        cov.build();
+        acceptances = rejections = 0;
+        acceptances_since_rebuild = 0;   // resetForRebuild keeps the streak
+        ++rebuilds;
+        rebuilt = true;
+      }
+      if (rebuilt || streak >= exhausted_streak) {
+        n += B - 1 - b;   // the rest of the batch was drawn from the old cover: discarded, its draws skipped
+        break;
+      }
+    }
+    // convergence test of the reference (SlqEngine.scala:249-262), here once per P retirements instead of per acceptance
+    THY_TRY(flush_evidence((long long)retired.size()));
+    if (processed > 0) {
+      double hmax = -INFINITY;
+      for (int a = 0; a < h->A; ++a) hmax = std::max(hmax, h->host_ao[(size_t)a * 2 + 1]);
+      if (processed > h->cfg.minIterationCount && std::isfinite(hmax) && (double)processed >= 10.0 * (double)P * hmax) converged = true;
+    }
+  }
+  converged = true;
+  THY_TRY(flush_evidence((long long)retired.size()));
+  // drain (SlqEngine.scala:171-180): the remaining pool in ascending order, one at a time
+  const long long live = (long long)retired.size();
+  std::vector<int> order(P);
+  for (int i = 0; i < P; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b2) { return key[a] < key[b2]; });
+  std::vector<double> tail(P);
+  for (int i = 0; i < P; ++i) tail[i] = key[order[i]];
+  if (live + P > h->ret_capacity) return fail(THY_ERR_STATE, "SLQ: retired buffer exhausted");
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_ll.ptr + live, tail.data(), (size_t)P * sizeof(double), cudaMemcpyHostToDevice, s));
+  THY_TRY(slq_evidence_launch(ev, h->A, P, h->P, 1, live, live, nullptr, h->seed, h->ret_ll.ptr + live, 1, s));
+  if (h->cfg.keepRetiredPoints) {
+    for (int i = 0; i < P; ++i)
+      retired_x.insert(retired_x.end(), cov.pt.begin() + (size_t)order[i] * d, cov.pt.begin() + (size_t)(order[i] + 1) * d);
+    THY_CUDA_CHECK(cudaMemcpyAsync(h->ret_x.ptr, retired_x.data(), retired_x.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  // the pool as it ended, back on the device
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->x.ptr, cov.pt.data(), (size_t)P * d * sizeof(double), cudaMemcpyHostToDevice, s));
+  THY_CUDA_CHECK(cudaMemcpyAsync(h->ll.ptr, key.data(), (size_t)P * sizeof(double), cudaMemcpyHostToDevice, s));
+  std::vector<double> ao((size_t)h->A * 2);
+  THY_CUDA_CHECK(cudaMemcpyAsync(ao.data(), h->abs_out.ptr, ao.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  THY_CUDA_CHECK(cudaStreamSynchronize(s));
+  h->live_iterations = live;
+  h->iterations = live + P;
+  h->rounds = n;   // proposals made
+  double mean = 0.0, m2 = 0.0, hm = 0.0;
+  for (int a = 0; a < h->A; ++a) { mean += ao[(size_t)a * 2]; hm += ao[(size_t)a * 2 + 1]; }
+  mean /= h->A;
+  hm /= h->A;
+  for (int a = 0; a < h->A; ++a) m2 += (ao[(size_t)a * 2] - mean) * (ao[(size_t)a * 2] - mean);
+  h->stats.iterations = live;
+  h->stats.total_retired = h->iterations;
+  h->stats.rounds = n;
+  h->stats.log_evidence_mean = mean;
+  h->stats.log_evidence_std = h->A > 1 ? std::sqrt(m2 / (h->A - 1)) : 0.0;
+  h->stats.neg_entropy_mean = hm;
+  h->stats.min_logpdf = tail[0];
+  h->stats.walk_scale = 1.0;                       // QuadratureDomainTelemetry.currentScaleFactor (rescaling disabled)
+  h->stats.walk_acceptance = n > 0 ? (double)live / (double)n : 0.0;
+  h->stats.likelihood_evaluations = h->evals;
+  h->ref_rebuilds = rebuilds;
+  h->finished = true;
   return THY_OK;
 }
 
@@ -631,6 +868,10 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   if (!(cfg->domainScalingIncrement > 0) || !(cfg->targetAcceptanceProbability > 0 && cfg->targetAcceptanceProbability < 1))
     return fail(THY_ERR_INVALID_ARGUMENT, "bad scaling increment / target acceptance");
   if (n_seeds < 0 || (n_seeds > 0 && !seeds)) return fail(THY_ERR_INVALID_ARGUMENT, "bad seeds");
+  if (cfg->referenceProposals) {
+    if (world != 1) return fail(THY_ERR_UNSUPPORTED, "referenceProposals (cubical cover) is a single-GPU, small-pool mode");
+    if (cfg->poolSize > 8192) return fail(THY_ERR_UNSUPPORTED, "referenceProposals: the cover's make-disjoint fold is O(P^2) and sequential; poolSize <= 8192");
+  }
   auto* h = new (std::nothrow) thy_slq_s();
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "allocation failed");
   h->model = m;
@@ -822,6 +1063,7 @@ thy_status thy_slq_run_rounds(thy_slq_t h, int n_rounds, int* out_converged) {
   thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (h->finished) return fail(THY_ERR_STATE, "the simulation has already been drained");
+  if (h->cfg.referenceProposals) return fail(THY_ERR_UNSUPPORTED, "referenceProposals runs as a whole (thy_slq_run)");
   bool conv = false;
   THY_TRY(slq_live_phase(h, n_rounds, &conv));
   if (out_converged) *out_converged = conv ? 1 : 0;
@@ -832,6 +1074,11 @@ thy_status thy_slq_run(thy_slq_t h, thy_slq_stats* out_stats) {
   thy::ErrScope _err_scope(h ? h->model : nullptr);
   if (!h) return fail(THY_ERR_INVALID_ARGUMENT, "null handle");
   if (h->finished) {
+    if (out_stats) *out_stats = h->stats;
+    return THY_OK;
+  }
+  if (h->cfg.referenceProposals) {
+    THY_TRY(slq_run_reference(h));
     if (out_stats) *out_stats = h->stats;
     return THY_OK;
   }

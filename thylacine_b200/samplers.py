@@ -281,7 +281,7 @@ class _SlqConfigC(C.Structure):
     _fields_ = [("poolSize", C.c_int), ("abscissaNumber", C.c_int), ("domainScalingIncrement", C.c_double),
                 ("targetAcceptanceProbability", C.c_double), ("sampleParallelism", C.c_int),
                 ("maxIterationCount", C.c_int), ("minIterationCount", C.c_int), ("constrainedWalkSteps", C.c_int),
-                ("keepRetiredPoints", C.c_int), ("disableFusedWalk", C.c_int)]
+                ("keepRetiredPoints", C.c_int), ("disableFusedWalk", C.c_int), ("referenceProposals", C.c_int)]
 
 
 class _SlqStatsC(C.Structure):
@@ -349,7 +349,8 @@ class SlqIntegratedPosterior:
     @classmethod
     def of(cls, slqConfig: SlqConfig, posterior: UnnormalisedPosterior, slqTelemetryUpdateCallback=None,
            domainRebuildStartCallback=None, domainRebuildFinishCallback=None, seedsSpec=None, rngSeed: int = 0,
-           comm=None, constrainedWalkSteps: int = 0, keepRetiredPoints: bool = False, fusedWalk: bool = True):
+           comm=None, constrainedWalkSteps: int = 0, keepRetiredPoints: bool = False, fusedWalk: bool = True,
+           referenceProposals: bool = False):
         self = object.__new__(cls)
         self.posterior, self.config, self.comm = posterior, slqConfig, comm
         self._cb = slqTelemetryUpdateCallback
@@ -357,7 +358,7 @@ class SlqIntegratedPosterior:
         cfg = _SlqConfigC(slqConfig.poolSize, slqConfig.abscissaNumber, float(slqConfig.domainScalingIncrement),
                           float(slqConfig.targetAcceptanceProbability), slqConfig.sampleParallelism,
                           slqConfig.maxIterationCount, slqConfig.minIterationCount, int(constrainedWalkSteps),
-                          1 if keepRetiredPoints else 0, 0 if fusedWalk else 1)
+                          1 if keepRetiredPoints else 0, 0 if fusedWalk else 1, 1 if referenceProposals else 0)
         seeds = None
         n_seeds = 0
         if seedsSpec:
