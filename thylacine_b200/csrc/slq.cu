@@ -71,7 +71,7 @@ struct thy_slq_s {
   bool fused_walk = false;             // slq_walk.cu covers this model: one kernel per round instead of 5 per walk step
   cudaStream_t side = nullptr;         // quadrature update runs beside the walk
   cudaStream_t side2 = nullptr;        // pool spread runs beside the all-gather and the selection
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_sigma = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_sigma = nullptr, ev_rng = nullptr;
   cudaEvent_t ev_round[3] = {};        // completion of round r is ev_round[r % 3]
   double* host_ao = nullptr;           // pinned [A][2] copy of abs_out
   int* host_c = nullptr;               // pinned copy of the local retire count (per-step path)
@@ -98,6 +98,7 @@ struct thy_slq_s {
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_fork2) cudaEventDestroy(ev_fork2);
     if (ev_sigma) cudaEventDestroy(ev_sigma);
+    if (ev_rng) cudaEventDestroy(ev_rng);
     for (auto& e : ev_round) if (e) cudaEventDestroy(e);
     for (auto& e : tev) if (e) cudaEventDestroy(e);
     if (host_ao) cudaFreeHost(host_ao);
@@ -287,14 +288,23 @@ __global__ void __launch_bounds__(256) k_slq_commit(int c, int d, const int* __r
 
 // scale *= (1 + inc) when the round's acceptance beat the target, else /= (1 + inc)   (SlqConfig.domainScalingIncrement,
 // targetAcceptanceProbability play the same role for the reference's cube scaling, QuadratureDomainTelemetry.scala)
+// counter != 0: the fused walk kernel has already summed the round's acceptances into accepted[0] (one integer atomic per
+// warp), so one warp suffices; otherwise accepted[w] holds per-walker tallies of the per-step kernels.
 __global__ void __launch_bounds__(1024) k_slq_adapt(double* scalars, double inc, double target, const int* __restrict__ c_dev,
-                                                    int steps, int* __restrict__ accepted) {
+                                                    int steps, int* __restrict__ accepted, int counter) {
   __shared__ double sh[32];
   const int c = *c_dev;
   double a = 0.0;
-  for (int w = threadIdx.x; w < c; w += blockDim.x) {
-    a += (double)accepted[w];
-    accepted[w] = 0;
+  if (counter) {
+    if (threadIdx.x == 0) {
+      a = (double)accepted[0];
+      accepted[0] = 0;
+    }
+  } else {
+    for (int w = threadIdx.x; w < c; w += blockDim.x) {
+      a += (double)accepted[w];
+      accepted[w] = 0;
+    }
   }
   a = warp_sum(a);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
@@ -410,10 +420,14 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   k_slq_sigma_final<<<(unsigned)ceil_div(d, 8), 256, 0, h->side2>>>(nrows, d, h->sig_part.ptr, nslab, h->sigma.ptr);
   count_launch(2);
   if (tracing) cudaEventRecord(h->tev[7], h->side2);
-  // the walk's randomness for this round, drawn while the main stream gathers and selects (sharded pools only)
-  if (h->fused_walk && h->pre_groups > 0)
-    THY_TRY(launch_slq_walk_rng(m, h->pre_groups, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->zpre.ptr, h->lacc.ptr, h->side2));
   THY_CUDA_CHECK(cudaEventRecord(h->ev_sigma, h->side2));
+  // the walk's randomness for this round, drawn while the main stream gathers and selects (sharded pools only), on the
+  // quadrature stream, which is idle until the selection has finished: beside the pool spread, not behind it
+  if (h->fused_walk && h->pre_groups > 0) {
+    THY_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork2, 0));
+    THY_TRY(launch_slq_walk_rng(m, h->pre_groups, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->zpre.ptr, h->lacc.ptr, h->side));
+    THY_CUDA_CHECK(cudaEventRecord(h->ev_rng, h->side));
+  }
   // ---- every rank sees every log-likelihood: ONE collective per round ----
   const double* keys = h->ll.ptr;
   if (h->world > 1) {
@@ -451,6 +465,7 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   }
   // ---- replacement: constrained walks from survivors ----
   THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sigma, 0));
+  if (h->fused_walk && h->pre_groups > 0) THY_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_rng, 0));
   if (h->fused_walk) {
     THY_TRY(launch_slq_walk(m, Kr, h->count_dev.ptr, h->Pl, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->sidx.ptr, h->flags.ptr,
                             h->x.ptr, h->ll.ptr, h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s,
@@ -482,8 +497,9 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
       count_launch();
     }
   }
-  k_slq_adapt<<<1, 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement, h->cfg.targetAcceptanceProbability,
-                                 h->count_dev.ptr, h->M, h->accepted.ptr);
+  k_slq_adapt<<<1, h->fused_walk ? 32 : 1024, 0, s>>>(h->scalars.ptr, h->cfg.domainScalingIncrement,
+                                                      h->cfg.targetAcceptanceProbability, h->count_dev.ptr, h->M,
+                                                      h->accepted.ptr, h->fused_walk ? 1 : 0);
   count_launch();
   // this rank's new keys go to every rank's staging area over NVLink; then the flag says so
   if (h->p2p) THY_TRY(slq_p2p_signal(h->p2p_view, h->Pl, h->sidx.ptr, h->ll.ptr, h->count_dev.ptr, h->ctl.ptr, s));
@@ -922,6 +938,7 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
               cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_sigma, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_rng, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost(&h->host_ao, (size_t)h->A * 2 * sizeof(double)) == cudaSuccess &&

@@ -18,7 +18,8 @@ namespace thy {
 
 namespace {
 
-constexpr int WNW = 8;  // warps per CTA
+constexpr int WNW = 6;  // warps per CTA (two CTAs per SM at <= 168 registers)
+constexpr int WCH = 8;  // 8-row blocks whose DMMA chains are interleaved; shared-memory rows are padded to 8 WCH
 
 struct WalkParams {
   const double* A;       // [n_pad][LDS]
@@ -40,11 +41,12 @@ struct WalkParams {
   double* lpr;           // [Pl]
   const double* sigma;   // [d]
   const double* scalars; // [0] walk scale, [1] threshold
-  int* accepted;         // [c] per-walker acceptance tally (+=)
+  int* accepted;         // [0] the round's acceptances over all walkers (one atomic per warp; k_slq_adapt reads and clears it)
   // pre-drawn randomness of this round for walker groups [0, pre_groups) (k_slq_walk_rng), or null: drawn in place
   const float* zpre;     // [group][M][KS][32] proposal normals in the walk kernel's lane order
   const double* lacc;    // [group][M][8] ln(1 - u) of the Metropolis test
   int pre_groups;
+  long long grp_begin, grp_end;   // walker groups this launch handles (pre-drawn launch: [0, pre_groups); in place: the rest)
 };
 
 // The walk's random numbers do not depend on its state.  With live points sharded over several GPUs a rank has few walkers
@@ -79,32 +81,40 @@ __global__ void __launch_bounds__(256) k_slq_walk_rng(int groups, int M, uint64_
   }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
+// Round 3 rewrite (profiles/r03_walk.md): the first version issued ~880 instructions per step of a group -- one LDS and a
+// WARPSYNC/NOP pair per predicated DMMA, 14 reconvergence regions for the prior kinds, shared-memory addresses rebuilt
+// from %tid inside the loop -- and a warp that runs alone on its scheduler (sharded pools) paid ~7 clocks for each.  Now:
+// row blocks come in unpredicated pairs (rows are padded to a multiple of 32 with zero coefficients and zero weights, so
+// a padding block adds exactly 0), the prior test is branch-free, PRE (randomness drawn ahead) is a template parameter so
+// the Philox path costs the pre-drawn instantiation neither registers nor instruction cache, the next step's normals are
+// fetched while the current step computes, and CTAs are 6 warps at <= 168 registers.  The arithmetic and its order are
+// unchanged: results are bit-identical to the first version.
+template <int NT, bool PRE>
+__global__ void __launch_bounds__(WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const WalkParams p) {
   constexpr int KS = 2 * NT;
   constexpr int LDS = 8 * NT + 4;
   extern __shared__ __align__(16) unsigned char smem[];
+  const int rows = (p.n_pad + 8 * WCH - 1) / (8 * WCH) * (8 * WCH);   // zero rows / zero weights beyond n_pad
   double* As = reinterpret_cast<double*>(smem);
-  double2* Ys = reinterpret_cast<double2*>(As + (size_t)p.n_pad * LDS);
-  double* sg = reinterpret_cast<double*>(Ys + p.n_pad);   // [8 NT] proposal scale per coordinate (0 beyond d)
-  double* p0 = sg + 8 * NT;
-  double* p1 = p0 + 8 * NT;
-  int* kind = reinterpret_cast<int*>(p1 + 8 * NT);
+  double2* Ys = reinterpret_cast<double2*>(As + (size_t)rows * LDS);
+  double4* pri = reinterpret_cast<double4*>(Ys + rows);   // [8 NT] (proposal scale, p0, p1, kind as a double)
+  double* xps_all = reinterpret_cast<double*>(pri + 8 * NT);   // [WNW][KS][32] the warps' proposals as DMMA A fragments
 
+  const int c = *p.c_dev;
+  const long long grp_end = min(p.grp_end, ((long long)c + 7) / 8);
+  if (p.grp_begin + (long long)blockIdx.x * WNW >= grp_end) return;   // nothing for this CTA (whole CTA: uniform)
   // ---- stage the model once per CTA ----
   {
     const double2* src = reinterpret_cast<const double2*>(p.A);
     double2* dst = reinterpret_cast<double2*>(As);
-    const int n2 = p.n_pad * LDS / 2;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = src[i];
-    for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) Ys[i] = p.yiv[i];
+    const int n2 = p.n_pad * LDS / 2, r2 = rows * LDS / 2;
+    for (int i = threadIdx.x; i < r2; i += blockDim.x) dst[i] = i < n2 ? src[i] : make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) Ys[i] = i < p.n_pad ? p.yiv[i] : make_double2(0.0, 0.0);
     const double scale = p.scalars[0];
     for (int j = threadIdx.x; j < 8 * NT; j += blockDim.x) {
       const bool in = j < p.d;
-      sg[j] = in ? scale * p.sigma[j] : 0.0;
-      p0[j] = in ? p.pr.p0[j] : 0.0;
-      p1[j] = in ? p.pr.p1[j] : 0.0;
-      kind[j] = in ? p.pr.kind[j] : -1;
+      pri[j] = make_double4(in ? scale * p.sigma[j] : 0.0, in ? p.pr.p0[j] : 0.0, in ? p.pr.p1[j] : 0.0,
+                            in ? (double)p.pr.kind[j] : -1.0);
     }
   }
   __syncthreads();
@@ -114,14 +124,20 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
   const int pi_g = (g8 < 4) ? g8 : (g8 ^ 1);                  // observation-row permutation of the fused kernel
   const int pi_s0 = (q4 < 2) ? (2 * q4) : (2 * q4 + 1);
   const int pi_s1 = (q4 < 2) ? (2 * q4 + 1) : (2 * q4);
-  const int off1 = pi_g * LDS + q4;
+  const double* Alane = As + pi_g * LDS + q4;
+  const double2* Y0 = Ys + pi_s0;
+  const double2* Y1 = Ys + pi_s1;
+  const double4* prl = pri + q4;
+  double* xps = xps_all + (size_t)warp * KS * 32 + lane;
   const double thr = p.scalars[1];
-  const int ngrp = (p.n + 7) / 8;   // row groups that hold observations (rows beyond n are zero padding)
-  const int d = p.d;
-  const int c = *p.c_dev;
+  const int nchunk = ((p.n + 7) / 8 + WCH - 1) / WCH;   // chunks of WCH 8-row blocks that hold observations
+  const int d = p.d, M = p.M;
   const uint64_t round = (uint64_t)*p.round_dev;
+  const bool gaussian = p.distribution == THY_DIST_GAUSSIAN;
+  const double log_const = p.log_const, prior_const = p.pr.log_const;
+  int acc_warp = 0;
 
-  for (long long grp = (long long)blockIdx.x * WNW + warp; grp * 8 < c; grp += (long long)gridDim.x * WNW) {
+  for (long long grp = p.grp_begin + (long long)blockIdx.x * WNW + warp; grp < grp_end; grp += (long long)gridDim.x * WNW) {
     const long long w = grp * 8 + g8;
     const bool live = w < c;
     const uint64_t key = ((uint64_t)p.rank << 40) | (uint64_t)(live ? w : 0);
@@ -143,23 +159,39 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
     double pcur = live ? p.lpr[src] : 0.0;
     int acc = 0;
 
-    const bool pre = p.zpre != nullptr && grp < p.pre_groups;
-    for (int step = 0; step < p.M; ++step) {
-      const uint64_t gstep = round * (uint64_t)p.M + (uint64_t)step;
-      const float* zrow = pre ? p.zpre + (((size_t)grp * p.M + step) * KS) * 32 + lane : nullptr;
-      float zf[KS];
-      if (pre) {
+    const float* zrow = nullptr;
+    const double* lrow = nullptr;
+    float zn[KS];
+    double ln = 0.0;
+    if (PRE) {
+      zrow = p.zpre + ((size_t)grp * M * KS) * 32 + lane;
+      lrow = p.lacc + (size_t)grp * M * 8 + g8;
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) zf[kk] = __ldg(zrow + (size_t)kk * 32);
+      for (int kk = 0; kk < KS; ++kk) zn[kk] = __ldg(zrow + kk * 32);
+      ln = __ldg(lrow);
+    }
+    for (int step = 0; step < M; ++step) {
+      const uint64_t gstep = round * (uint64_t)M + (uint64_t)step;
+      float zf[KS];
+      double lu = ln;
+      if (PRE) {
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) zf[kk] = zn[kk];
+        if (step + 1 < M) {   // the next step's randomness travels while this step computes
+          zrow += KS * 32;
+          lrow += 8;
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk) zn[kk] = __ldg(zrow + kk * 32);
+          ln = __ldg(lrow);
+        }
       }
-      const double lthr = pre ? p.lacc[((size_t)grp * p.M + step) * 8 + g8] : 0.0;
-      // ---- propose + prior of the proposal ----
+      // ---- propose + prior of the proposal (branch-free over the prior kinds) ----
       double pacc = 0.0;
-      bool inside = true;
+      int outside = 0;   // integer logic: `&&` would compile to one reconvergence region per coordinate
 #pragma unroll
       for (int kk = 0; kk < KS; kk += 2) {
         double z0, z1;
-        if (pre) {
+        if (PRE) {
           z0 = (double)zf[kk];
           z1 = (double)zf[kk + 1];
         } else {
@@ -167,55 +199,56 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int k = 4 * (kk + h) + q4;
-          const double v = xf[kk + h] + sg[k] * (h == 0 ? z0 : z1);
+          const double4 pk = prl[4 * (kk + h)];
+          const double v = xf[kk + h] + pk.x * (h == 0 ? z0 : z1);
           xp[kk + h] = v;
-          const int kd = kind[k];
-          if (kd == PK_GAUSS_DIAG) {
-            const double dl = p0[k] - v;
-            pacc += dl * (dl * p1[k]);
-          } else if (kd == PK_UNIFORM) {
-            inside = inside && (v >= p0[k]) && (v < p1[k]);
-          }
+          xps[(kk + h) * 32] = v;
+          const double dl = pk.y - v;
+          const double gq = dl * (dl * pk.z);
+          pacc += (pk.w == (double)PK_GAUSS_DIAG) ? gq : 0.0;
+          outside |= (int)(pk.w == (double)PK_UNIFORM) & ((int)!(v >= pk.y) | (int)!(v < pk.z));
         }
       }
       pacc = quad_sum(pacc);
-      const unsigned ballot = __ballot_sync(0xffffffffu, inside);
+      const unsigned ballot = __ballot_sync(0xffffffffu, outside == 0);
       const bool inside_all = ((ballot >> (lane & ~3)) & 0xFu) == 0xFu;
-      const double lpn = inside_all ? (-0.5 * pacc + p.pr.log_const) : -INFINITY;
-      // ---- forward pass on the tensor cores, residual quadratic form ----
-      // (Eight independent accumulator chains per block instead of two were measured and dropped: 1276 vs 1155 us per
-      // round at 62 500 walkers, 299 vs 284 us at 7 812 -- the step is bound by its ~1600 dependent scalar instructions,
-      // Philox and the prior test, not by the DMMA chain; profiles/r02_ncu_walk_low_occupancy.json.)
+      const double lpn = inside_all ? (-0.5 * pacc + prior_const) : -INFINITY;
+      // ---- forward pass on the tensor cores, residual quadratic form: WCH independent 8-row blocks at a time ----
+      // A DMMA.8x8x4 that depends on its predecessor issues ~48 clocks after it, an independent one every ~16
+      // (profiles/r03_walk.md).  ptxas reorders unrolled mma.sync sequences into one serial chain per accumulator whatever
+      // order the PTX has, so the K loop is kept ROLLED: one iteration = one K-slice of all WCH row blocks, WCH
+      // independent DMMAs that cannot be regrouped across the back edge.  The proposal comes back from shared memory
+      // (a rolled loop cannot index registers); each lane reads only what it wrote itself.
       double ssq = 0.0;
-      for (int j = 0; j < ngrp; j += 2) {
-        double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;
-        const double* Aj = As + (size_t)j * 8 * LDS + off1;
-        const bool two = (j + 1) < ngrp;
+      const double* Aj = Alane;
+      const double2 *y0p = Y0, *y1p = Y1;
+      for (int jc = 0; jc < nchunk; ++jc, Aj += WCH * 8 * LDS, y0p += WCH * 8, y1p += WCH * 8) {
+        double z0[WCH], z1[WCH];
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {
-          ptx::dmma884(za0, za1, xp[kk], Aj[4 * kk]);
-          if (two) ptx::dmma884(zb0, zb1, xp[kk], Aj[8 * LDS + 4 * kk]);
+        for (int cb = 0; cb < WCH; ++cb) z0[cb] = z1[cb] = 0.0;
+        const double* bp = Aj;
+        const double* xq = xps;
+#pragma unroll 1
+        for (int kk = 0; kk < KS; ++kk, bp += 4, xq += 32) {
+          const double a = *xq;
+          double b[WCH];
+#pragma unroll
+          for (int cb = 0; cb < WCH; ++cb) b[cb] = bp[cb * 8 * LDS];
+#pragma unroll
+          for (int cb = 0; cb < WCH; ++cb) ptx::dmma884(z0[cb], z1[cb], a, b[cb]);
         }
-        {
-          const double2 y0 = Ys[j * 8 + pi_s0], y1 = Ys[j * 8 + pi_s1];
-          const double r0 = y0.x - za0, r1 = y1.x - za1;
-          ssq = fma(r0, r0 * y0.y, ssq);
-          ssq = fma(r1, r1 * y1.y, ssq);
-        }
-        if (two) {
-          const double2 y0 = Ys[(j + 1) * 8 + pi_s0], y1 = Ys[(j + 1) * 8 + pi_s1];
-          const double r0 = y0.x - zb0, r1 = y1.x - zb1;
+#pragma unroll
+        for (int cb = 0; cb < WCH; ++cb) {
+          const double2 y0 = y0p[cb * 8], y1 = y1p[cb * 8];
+          const double r0 = y0.x - z0[cb], r1 = y1.x - z1[cb];
           ssq = fma(r0, r0 * y0.y, ssq);
           ssq = fma(r1, r1 * y1.y, ssq);
         }
       }
       const double q = quad_sum(ssq);
-      const double lnew = (p.distribution == THY_DIST_GAUSSIAN) ? (-0.5 * q + p.log_const)
-                                                                : (p.log_const - (1.0 + p.n) / 2.0 * log(1.0 + q));
+      const double lnew = gaussian ? (-0.5 * q + log_const) : (log_const - (1.0 + p.n) / 2.0 * log(1.0 + q));
       // ---- Metropolis test w.r.t. the prior, hard likelihood constraint (same draw as k_slq_accept) ----
-      double lu = lthr;
-      if (!pre) {
+      if (!PRE) {
         const RngDraw u = rng_uniform2(p.seed, key, 0, RNG_SLQ_ACCEPT, gstep);
         lu = log(1.0 - u.u0);
       }
@@ -238,32 +271,47 @@ __global__ void __launch_bounds__(WNW * 32) k_slq_walk(const WalkParams p) {
       if (q4 == 0) {
         p.ll[slot] = lcur;
         p.lpr[slot] = pcur;
-        p.accepted[w] += acc;
       }
     }
+    acc_warp += __reduce_add_sync(0xffffffffu, (live && q4 == 0) ? acc : 0);
   }
+  if (lane == 0 && acc_warp != 0) atomicAdd(p.accepted, acc_warp);
 }
 
-template <int NT>
-thy_status launch_walk_nt(const WalkParams& p, int c_max, size_t smem, cudaStream_t s) {
-  THY_CUDA_CHECK(cudaFuncSetAttribute(k_slq_walk<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NT, bool PRE>
+thy_status launch_walk_pre(WalkParams p, long long grp_begin, long long grp_end, size_t smem, cudaStream_t s) {
+  if (grp_end <= grp_begin) return THY_OK;
+  p.grp_begin = grp_begin;
+  p.grp_end = grp_end;
+  THY_CUDA_CHECK(cudaFuncSetAttribute(k_slq_walk<NT, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  THY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_slq_walk<NT>, WNW * 32, smem));
+  THY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_slq_walk<NT, PRE>, WNW * 32, smem));
   if (per_sm < 1) per_sm = 1;
   // sized for the largest possible retire count; the kernel reads the actual one from device memory (grid-stride loop)
-  const long long groups = (c_max + 7) / 8;
-  long long blocks = (groups + WNW - 1) / WNW;
+  long long blocks = (grp_end - grp_begin + WNW - 1) / WNW;
   const long long cap = (long long)sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
-  k_slq_walk<NT><<<(unsigned)blocks, WNW * 32, smem, s>>>(p);
+  k_slq_walk<NT, PRE><<<(unsigned)blocks, WNW * 32, smem, s>>>(p);
   count_launch();
   THY_CUDA_CHECK(cudaGetLastError());
   return THY_OK;
 }
 
+// Groups [0, pre_groups) read the randomness drawn ahead; the rest (none, unless a rank replaces more than 1.25x its share
+// of a round) draw in place.  Both launches read the actual walker count from device memory; a CTA with nothing to do
+// returns before it stages the model.
+template <int NT>
+thy_status launch_walk_nt(const WalkParams& p, int c_max, size_t smem, cudaStream_t s) {
+  const long long groups = (c_max + 7) / 8;
+  const long long pre = p.zpre ? std::min<long long>(p.pre_groups, groups) : 0;
+  THY_TRY((launch_walk_pre<NT, true>(p, 0, pre, smem, s)));
+  return launch_walk_pre<NT, false>(p, pre, groups, smem, s);
+}
+
 size_t walk_smem_bytes(const LikDev& lk, int nt) {
   const int LDS = 8 * nt + 4;
-  return (size_t)lk.n_pad * LDS * 8 + (size_t)lk.n_pad * 16 + (size_t)8 * nt * (3 * 8 + 4) + 16;
+  const size_t rows = (size_t)round_up(lk.n_pad, 8 * WCH);
+  return rows * LDS * 8 + rows * 16 + (size_t)8 * nt * 32 + (size_t)WNW * 2 * nt * 32 * 8 + 16;
 }
 
 }  // namespace
