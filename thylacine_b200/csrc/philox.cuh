@@ -68,28 +68,32 @@ __host__ __device__ inline double rng_normal(uint64_t seed, uint64_t chain, uint
   return r * cospi(2.0 * d.u1);
 }
 
-// SLQ random-walk proposals: TWO standard normals per Philox call (both Box-Muller branches), evaluated with fp32
-// special functions (MUFU log / sincospi).  A proposal only has to be symmetric and cheap -- its 24-bit resolution and
-// the +-5.8 sigma truncation do not enter the acceptance test, which stays in fp64.  ~6x cheaper than rng_normal.
+// SLQ random-walk proposals: FOUR standard normals per Philox call (both Box-Muller branches of two (radius, angle)
+// pairs; every word of the 4x32 output is used), evaluated with fp32 special functions (MUFU log / sincospi).  A proposal
+// only has to be symmetric and cheap -- its 24-bit resolution and the +-5.8 sigma truncation do not enter the acceptance
+// test, which stays in fp64.  ~10x cheaper per normal than rng_normal.
 #ifdef __CUDACC__
-__device__ __forceinline__ void rng_normal_pair_fast(uint64_t seed, uint64_t chain, uint32_t item, uint32_t purpose,
-                                                     uint64_t step, double& z0, double& z1) {
+__device__ __forceinline__ void rng_normal_quad_fast(uint64_t seed, uint64_t chain, uint32_t item, uint32_t purpose,
+                                                     uint64_t step, double (&z)[4]) {
   uint32_t r[4];
   const uint32_t k0 = (uint32_t)seed ^ (uint32_t)(chain >> 32) * 0x85EBCA6Bu;
   const uint32_t k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32) * 0xC2B2AE35u;
   Philox::gen((uint32_t)chain, item, (uint32_t)step, purpose, k0, k1, r);
-  const float u = (float)((r[0] >> 8) + 1u) * (1.0f / 16777216.0f);   // (0, 1]
-  const float v = (float)(r[2] >> 8) * (1.0f / 8388608.0f);           // [0, 2): angle / pi
-  const float rad = sqrtf(-2.0f * __logf(u));
-  float sn, cs;
-  sincospif(v, &sn, &cs);
-  z0 = (double)(rad * cs);
-  z1 = (double)(rad * sn);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u = (float)((r[2 * h] >> 8) + 1u) * (1.0f / 16777216.0f);   // (0, 1]
+    const float v = (float)(r[2 * h + 1] >> 8) * (1.0f / 8388608.0f);       // [0, 2): angle / pi
+    const float rad = sqrtf(-2.0f * __logf(u));
+    float sn, cs;
+    sincospif(v, &sn, &cs);
+    z[2 * h] = (double)(rad * cs);
+    z[2 * h + 1] = (double)(rad * sn);
+  }
 }
 #endif
-// coordinate j of a walker -> (item, branch) of its proposal pair: lanes of the fused walk kernel own coordinates
-// 4 kk + q, so pairing kk with kk + 1 keeps both branches of a pair in one thread
-__host__ __device__ inline uint32_t slq_move_item(int j) { return (uint32_t)(((j >> 3) << 2) | (j & 3)); }
-__host__ __device__ inline int slq_move_branch(int j) { return (j >> 2) & 1; }
+// coordinate j of a walker -> (item, branch) of its proposal quadruple: lanes of the fused walk kernel own coordinates
+// 4 kk + q, so grouping kk, kk + 1, kk + 2, kk + 3 keeps all four normals of a call in one thread
+__host__ __device__ inline uint32_t slq_move_item(int j) { return (uint32_t)(((j >> 4) << 2) | (j & 3)); }
+__host__ __device__ inline int slq_move_branch(int j) { return (j >> 2) & 3; }
 
 }  // namespace thy

@@ -242,8 +242,10 @@ __global__ void __launch_bounds__(256) k_slq_propose(int c, int d, uint64_t seed
   if (i >= (long long)c * d) return;
   const int w = (int)(i / d), j = (int)(i % d);
   double z0, z1;
-  rng_normal_pair_fast(seed, ((uint64_t)rank << 40) | (uint64_t)w, slq_move_item(j), RNG_SLQ_MOVE, step, z0, z1);
-  Yp[i] = Y[i] + scalars[0] * sigma[j] * (slq_move_branch(j) ? z1 : z0);
+  double z[4];
+  rng_normal_quad_fast(seed, ((uint64_t)rank << 40) | (uint64_t)w, slq_move_item(j), RNG_SLQ_MOVE, step, z);
+  const int br = slq_move_branch(j);
+  Yp[i] = Y[i] + scalars[0] * sigma[j] * (br == 0 ? z[0] : br == 1 ? z[1] : br == 2 ? z[2] : z[3]);
 }
 
 // Metropolis test w.r.t. the prior, hard likelihood constraint L' > L*.
@@ -948,10 +950,13 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     if (!ok) st = fail(THY_ERR_CUDA, "SLQ stream / event setup failed");
     else *h->host_conv = -1;
     h->fused_walk = !cfg->disableFusedWalk && slq_walk_supported(m);
-    // Sharded pool: a rank replaces ~K / world points per round and its walk is latency-bound, so the walk's randomness is
-    // drawn ahead on a side stream for 1.25 K / world + 64 walkers (the rest, if a rank ever has more, draw in place).
-    const char* pre_env = std::getenv("THY_SLQ_PREDRAW");   // 0 / 1 force off / on (measurement knob)
-    const bool predraw = pre_env ? pre_env[0] == '1' : world > 1;
+    // THY_SLQ_PREDRAW=1 draws a round's walk randomness ahead on a side stream (k_slq_walk_rng) for 1.25 K / world + 64
+    // walkers (the rest, if a rank ever has more, draw in place).  Round 2 made it the default for sharded pools; since
+    // the walk kernel draws four normals per Philox call and its in-place instantiation runs 16 warps per SM the
+    // in-place form is faster at every size measured (125 000-point shard: 241 vs 281 us per round; 10^6: 1089 vs
+    // 1202 us), so it is now an option only (profiles/r03_walk.md).
+    const char* pre_env = std::getenv("THY_SLQ_PREDRAW");
+    const bool predraw = pre_env && pre_env[0] == '1';
     if (h->fused_walk && predraw && st == THY_OK) {
       const long long walkers = std::min<long long>(K, (5LL * K) / (4LL * world) + 64);
       h->pre_groups = (int)((walkers + 7) / 8);

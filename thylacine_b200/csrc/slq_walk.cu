@@ -18,7 +18,10 @@ namespace thy {
 
 namespace {
 
-constexpr int WNW = 6;  // warps per CTA (two CTAs per SM at <= 168 registers)
+constexpr int WNW_MAX = 8;
+// warps per CTA: 6 for the pre-drawn instantiation (two CTAs per SM at <= 168 registers: few walkers, latency matters),
+// 8 when the randomness is drawn in place (two CTAs per SM at <= 128 registers: many walkers, occupancy matters)
+template <bool PRE> struct WalkCta { static constexpr int WNW = PRE ? 6 : 8; };
 constexpr int WCH = 8;  // 8-row blocks whose DMMA chains are interleaved; shared-memory rows are padded to 8 WCH
 
 struct WalkParams {
@@ -69,11 +72,12 @@ __global__ void __launch_bounds__(256) k_slq_walk_rng(int groups, int M, uint64_
   const uint64_t gstep = (uint64_t)*round_dev * (uint64_t)M + (uint64_t)step;
   float* zrow = zpre + ((size_t)wid * KS) * 32 + lane;
 #pragma unroll
-  for (int kk = 0; kk < KS; kk += 2) {
-    double z0, z1;
-    rng_normal_pair_fast(seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z0, z1);
-    zrow[(size_t)kk * 32] = (float)z0;         // z0, z1 are fp32 values widened to double: the round trip is exact
-    zrow[(size_t)(kk + 1) * 32] = (float)z1;
+  for (int kk = 0; kk < KS; kk += 4) {
+    double z[4];
+    rng_normal_quad_fast(seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z);
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      if (kk + h < KS) zrow[(size_t)(kk + h) * 32] = (float)z[h];   // fp32 values widened to double: the round trip is exact
   }
   if (q4 == 0) {
     const RngDraw u = rng_uniform2(seed, key, 0, RNG_SLQ_ACCEPT, gstep);
@@ -90,7 +94,8 @@ __global__ void __launch_bounds__(256) k_slq_walk_rng(int groups, int M, uint64_
 // fetched while the current step computes, and CTAs are 6 warps at <= 168 registers.  The arithmetic and its order are
 // unchanged: results are bit-identical to the first version.
 template <int NT, bool PRE>
-__global__ void __launch_bounds__(WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const WalkParams p) {
+__global__ void __launch_bounds__(WalkCta<PRE>::WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const WalkParams p) {
+  constexpr int WNW = WalkCta<PRE>::WNW;
   constexpr int KS = 2 * NT;
   constexpr int LDS = 8 * NT + 4;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const 
       slot = p.sidx[w];
     }
     src = __shfl_sync(0xffffffffu, src, lane & ~3);   // one lane of the quad draws, the quad shares the pick
-    double xf[KS], xp[KS];
+    double xf[KS];   // the proposal lives in shared memory only (xps): 2 KS fewer registers per thread
 #pragma unroll
     for (int kk = 0; kk < KS; ++kk) {
       const int k = 4 * kk + q4;
@@ -189,24 +194,25 @@ __global__ void __launch_bounds__(WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const 
       double pacc = 0.0;
       int outside = 0;   // integer logic: `&&` would compile to one reconvergence region per coordinate
 #pragma unroll
-      for (int kk = 0; kk < KS; kk += 2) {
-        double z0, z1;
+      for (int kk = 0; kk < KS; kk += 4) {
+        double z[4];
         if (PRE) {
-          z0 = (double)zf[kk];
-          z1 = (double)zf[kk + 1];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) z[h] = (kk + h < KS) ? (double)zf[(kk + h < KS) ? kk + h : 0] : 0.0;
         } else {
-          rng_normal_pair_fast(p.seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z0, z1);
+          rng_normal_quad_fast(p.seed, key, slq_move_item(4 * kk + q4), RNG_SLQ_MOVE, gstep, z);
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const double4 pk = prl[4 * (kk + h)];
-          const double v = xf[kk + h] + pk.x * (h == 0 ? z0 : z1);
-          xp[kk + h] = v;
-          xps[(kk + h) * 32] = v;
-          const double dl = pk.y - v;
-          const double gq = dl * (dl * pk.z);
-          pacc += (pk.w == (double)PK_GAUSS_DIAG) ? gq : 0.0;
-          outside |= (int)(pk.w == (double)PK_UNIFORM) & ((int)!(v >= pk.y) | (int)!(v < pk.z));
+        for (int h = 0; h < 4; ++h) {
+          if (kk + h < KS) {
+            const double4 pk = prl[4 * (kk + h)];
+            const double v = xf[kk + h] + pk.x * z[h];
+            xps[(kk + h) * 32] = v;
+            const double dl = pk.y - v;
+            const double gq = dl * (dl * pk.z);
+            pacc += (pk.w == (double)PK_GAUSS_DIAG) ? gq : 0.0;
+            outside |= (int)(pk.w == (double)PK_UNIFORM) & ((int)!(v >= pk.y) | (int)!(v < pk.z));
+          }
         }
       }
       pacc = quad_sum(pacc);
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const 
       const bool ok = live && isfinite(lpn) && isfinite(lnew) && (lnew > thr) && (lpn - pcur >= lu);
       if (ok) {
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) xf[kk] = xp[kk];
+        for (int kk = 0; kk < KS; ++kk) xf[kk] = xps[kk * 32];
         lcur = lnew;
         pcur = lpn;
         ++acc;
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const 
 
 template <int NT, bool PRE>
 thy_status launch_walk_pre(WalkParams p, long long grp_begin, long long grp_end, size_t smem, cudaStream_t s) {
+  constexpr int WNW = WalkCta<PRE>::WNW;
   if (grp_end <= grp_begin) return THY_OK;
   p.grp_begin = grp_begin;
   p.grp_end = grp_end;
@@ -311,7 +318,7 @@ thy_status launch_walk_nt(const WalkParams& p, int c_max, size_t smem, cudaStrea
 size_t walk_smem_bytes(const LikDev& lk, int nt) {
   const int LDS = 8 * nt + 4;
   const size_t rows = (size_t)round_up(lk.n_pad, 8 * WCH);
-  return rows * LDS * 8 + rows * 16 + (size_t)8 * nt * 32 + (size_t)WNW * 2 * nt * 32 * 8 + 16;
+  return rows * LDS * 8 + rows * 16 + (size_t)8 * nt * 32 + (size_t)WNW_MAX * 2 * nt * 32 * 8 + 16;
 }
 
 }  // namespace
