@@ -954,7 +954,7 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
     // walkers (the rest, if a rank ever has more, draw in place).  Round 2 made it the default for sharded pools; since
     // the walk kernel draws four normals per Philox call and its in-place instantiation runs 16 warps per SM the
     // in-place form is faster at every size measured (125 000-point shard: 241 vs 281 us per round; 10^6: 1089 vs
-    // 1202 us), so it is now an option only (profiles/r03_walk.md).
+    // 1202 us), so it is now an option only (profiles/r02_walk_rewrite.md).
     const char* pre_env = std::getenv("THY_SLQ_PREDRAW");
     const bool predraw = pre_env && pre_env[0] == '1';
     if (h->fused_walk && predraw && st == THY_OK) {

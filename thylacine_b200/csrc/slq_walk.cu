@@ -85,14 +85,14 @@ __global__ void __launch_bounds__(256) k_slq_walk_rng(int groups, int M, uint64_
   }
 }
 
-// Round 3 rewrite (profiles/r03_walk.md): the first version issued ~880 instructions per step of a group -- one LDS and a
-// WARPSYNC/NOP pair per predicated DMMA, 14 reconvergence regions for the prior kinds, shared-memory addresses rebuilt
-// from %tid inside the loop -- and a warp that runs alone on its scheduler (sharded pools) paid ~7 clocks for each.  Now:
-// row blocks come in unpredicated pairs (rows are padded to a multiple of 32 with zero coefficients and zero weights, so
-// a padding block adds exactly 0), the prior test is branch-free, PRE (randomness drawn ahead) is a template parameter so
-// the Philox path costs the pre-drawn instantiation neither registers nor instruction cache, the next step's normals are
-// fetched while the current step computes, and CTAs are 6 warps at <= 168 registers.  The arithmetic and its order are
-// unchanged: results are bit-identical to the first version.
+// Second version (round 2, profiles/r02_walk_rewrite.md).  The first issued ~880 instructions per step of a group -- one
+// LDS and a WARPSYNC/NOP pair per predicated DMMA, 14 reconvergence regions for the prior kinds, shared-memory addresses
+// rebuilt from %tid inside the loop -- plus ~950 for seven Philox calls when the randomness is drawn in place.  Now: row
+// blocks come in unpredicated groups of WCH (shared-memory rows are padded with zero coefficients and zero weights, so a
+// padding block adds exactly 0), the prior test is branch-free, four proposal normals come from one Philox call, PRE
+// (randomness drawn ahead) is a template parameter so neither instantiation carries the other's registers or code, the
+// proposal lives in shared memory only, and the round's acceptances leave through one integer atomic per warp.  The
+// arithmetic of a step and its order are unchanged; the proposal normals are a different (equally valid) stream.
 template <int NT, bool PRE>
 __global__ void __launch_bounds__(WalkCta<PRE>::WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const WalkParams p) {
   constexpr int WNW = WalkCta<PRE>::WNW;
@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(WalkCta<PRE>::WNW * 32, (NT <= 7) ? 2 : 1) k_s
       const bool inside_all = ((ballot >> (lane & ~3)) & 0xFu) == 0xFu;
       const double lpn = inside_all ? (-0.5 * pacc + prior_const) : -INFINITY;
       // ---- forward pass on the tensor cores, residual quadratic form: WCH independent 8-row blocks at a time ----
-      // A DMMA.8x8x4 that depends on its predecessor issues ~48 clocks after it, an independent one every ~16
-      // (profiles/r03_walk.md).  ptxas reorders unrolled mma.sync sequences into one serial chain per accumulator whatever
-      // order the PTX has, so the K loop is kept ROLLED: one iteration = one K-slice of all WCH row blocks, WCH
-      // independent DMMAs that cannot be regrouped across the back edge.  The proposal comes back from shared memory
-      // (a rolled loop cannot index registers); each lane reads only what it wrote itself.
+      // The K loop is kept ROLLED: one iteration = one K-slice of all WCH row blocks, i.e. WCH independent DMMAs (one warp
+      // issues a DMMA.8x8x4 every 26 clocks down a dependent chain and every 18.5 across independent ones,
+      // profiles/r02_dmma_issue_model.jsonl; ptxas regroups an unrolled sequence into one serial chain per accumulator
+      // whatever order the PTX has).  It is also a third of the code of the unrolled form.  The proposal comes back from
+      // shared memory (a rolled loop cannot index registers); each lane reads only what it wrote itself.
       double ssq = 0.0;
       const double* Aj = Alane;
       const double2 *y0p = Y0, *y1p = Y1;
