@@ -64,7 +64,8 @@ bool slq_walk_supported(const thy_model_s* m);
 thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long long Pl, int M, uint64_t seed,
                            const long long* round_dev, int rank, const int* sidx, const unsigned char* flags, double* x,
                            double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s,
-                           const float* zpre = nullptr, const double* lacc = nullptr, int pre_groups = 0);
+                           const float* zpre = nullptr, const double* lacc = nullptr, int pre_groups = 0,
+                           int expected = 0);   // walkers expected on this rank (sizes the CTAs; 0 = c_max)
 // the round's proposal normals / acceptance thresholds for walker groups [0, groups), drawn ahead of the walk
 size_t slq_walk_rng_floats_per_group(const thy_model_s* m, int M);
 thy_status launch_slq_walk_rng(thy_model_s* m, int groups, int M, uint64_t seed, const long long* round_dev, int rank,

@@ -471,7 +471,8 @@ static thy_status slq_round_enqueue(thy_slq_s* h, int Kr, cudaStream_t s, bool t
   if (h->fused_walk) {
     THY_TRY(launch_slq_walk(m, Kr, h->count_dev.ptr, h->Pl, h->M, h->seed, h->ctl.ptr + 1, h->rank, h->sidx.ptr, h->flags.ptr,
                             h->x.ptr, h->ll.ptr, h->lpr.ptr, h->sigma.ptr, h->scalars.ptr, h->accepted.ptr, s,
-                            h->pre_groups > 0 ? h->zpre.ptr : nullptr, h->lacc.ptr, h->pre_groups));
+                            h->pre_groups > 0 ? h->zpre.ptr : nullptr, h->lacc.ptr, h->pre_groups,
+                            (int)std::min<long long>(Kr, ((long long)Kr + h->world - 1) / h->world)));
   } else {
     int c = Kr;   // single GPU: every retiree is local
     if (h->world > 1) {

@@ -18,10 +18,13 @@ namespace thy {
 
 namespace {
 
-constexpr int WNW_MAX = 8;
-// warps per CTA: 6 for the pre-drawn instantiation (two CTAs per SM at <= 168 registers: few walkers, latency matters),
-// 8 when the randomness is drawn in place (two CTAs per SM at <= 128 registers: many walkers, occupancy matters)
-template <bool PRE> struct WalkCta { static constexpr int WNW = PRE ? 6 : 8; };
+// ONE CTA per SM, its width chosen per launch (walk_cta_warps): a rank that replaces few points spreads its walker groups
+// evenly over the SMs -- two CTAs landing on one SM put three warps on a scheduler there, and the kernel ends with its
+// slowest warp (DMMA.8x8x4 issues every 26 / 33 / 50 clocks per warp with 1 / 2 / 3 warps on a scheduler,
+// profiles/r02_dmma_issue_model.jsonl).  Widest CTA: 12 warps at <= 170 registers with the randomness drawn ahead,
+// 16 at <= 128 when it is drawn in place; 8 for wide models (NT > 7), whose state needs up to 255 registers.
+template <int NT, bool PRE> struct WalkCta { static constexpr int MAXW = (NT > 7) ? 8 : (PRE ? 12 : 16); };
+constexpr int WNW_MIN = 8;   // the width slq_walk_supported() budgets shared memory for
 constexpr int WCH = 8;  // 8-row blocks whose DMMA chains are interleaved; shared-memory rows are padded to 8 WCH
 
 struct WalkParams {
@@ -94,8 +97,8 @@ __global__ void __launch_bounds__(256) k_slq_walk_rng(int groups, int M, uint64_
 // proposal lives in shared memory only, and the round's acceptances leave through one integer atomic per warp.  The
 // arithmetic of a step and its order are unchanged; the proposal normals are a different (equally valid) stream.
 template <int NT, bool PRE>
-__global__ void __launch_bounds__(WalkCta<PRE>::WNW * 32, (NT <= 7) ? 2 : 1) k_slq_walk(const WalkParams p) {
-  constexpr int WNW = WalkCta<PRE>::WNW;
+__global__ void __launch_bounds__(WalkCta<NT, PRE>::MAXW * 32, 1) k_slq_walk(const WalkParams p) {
+  const int WNW = blockDim.x >> 5;
   constexpr int KS = 2 * NT;
   constexpr int LDS = 8 * NT + 4;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -284,21 +287,38 @@ __global__ void __launch_bounds__(WalkCta<PRE>::WNW * 32, (NT <= 7) ? 2 : 1) k_s
   if (lane == 0 && acc_warp != 0) atomicAdd(p.accepted, acc_warp);
 }
 
+size_t walk_smem_bytes(const LikDev& lk, int nt, int warps) {
+  const int LDS = 8 * nt + 4;
+  const size_t rows = (size_t)round_up(lk.n_pad, 8 * WCH);
+  return rows * LDS * 8 + rows * 16 + (size_t)8 * nt * 32 + (size_t)warps * 2 * nt * 32 * 8 + 16;
+}
+constexpr size_t WALK_SMEM_BUDGET = (size_t)200 * 1024;
+
+// CTA shape for `groups` walker groups expected on this rank.  One pass over the SMs suffices: ONE CTA per SM, as narrow
+// as holds them, so the groups spread evenly.  Otherwise: two CTAs of maxw / 2 warps per SM and a grid-stride loop (measured
+// at 7 813 groups: 1 044-1 089 us per round against 1 213 for one 14-warp CTA per SM that wastes less of its last pass).
+struct WalkShape { int warps, ctas_per_sm; };
+WalkShape walk_cta_shape(long long groups, int sms, int maxw) {
+  if (groups <= (long long)sms * maxw) return {(int)std::max<long long>(1, (groups + sms - 1) / sms), 1};
+  return {maxw / 2, 2};
+}
+
 template <int NT, bool PRE>
-thy_status launch_walk_pre(WalkParams p, long long grp_begin, long long grp_end, size_t smem, cudaStream_t s) {
-  constexpr int WNW = WalkCta<PRE>::WNW;
+thy_status launch_walk_pre(WalkParams p, const LikDev& lk, long long grp_begin, long long grp_end, long long expected_groups,
+                           cudaStream_t s) {
   if (grp_end <= grp_begin) return THY_OK;
   p.grp_begin = grp_begin;
   p.grp_end = grp_end;
+  const int sms = sm_count();
+  const WalkShape shape = walk_cta_shape(std::min(expected_groups, grp_end - grp_begin), sms, WalkCta<NT, PRE>::MAXW);
+  int warps = shape.warps;
+  while (warps > 1 && walk_smem_bytes(lk, NT, warps) * shape.ctas_per_sm > WALK_SMEM_BUDGET) --warps;
+  const size_t smem = walk_smem_bytes(lk, NT, warps);
   THY_CUDA_CHECK(cudaFuncSetAttribute(k_slq_walk<NT, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  THY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_slq_walk<NT, PRE>, WNW * 32, smem));
-  if (per_sm < 1) per_sm = 1;
   // sized for the largest possible retire count; the kernel reads the actual one from device memory (grid-stride loop)
-  long long blocks = (grp_end - grp_begin + WNW - 1) / WNW;
-  const long long cap = (long long)sm_count() * per_sm;
-  if (blocks > cap) blocks = cap;
-  k_slq_walk<NT, PRE><<<(unsigned)blocks, WNW * 32, smem, s>>>(p);
+  long long blocks = (grp_end - grp_begin + warps - 1) / warps;
+  if (blocks > (long long)sms * shape.ctas_per_sm) blocks = (long long)sms * shape.ctas_per_sm;
+  k_slq_walk<NT, PRE><<<(unsigned)blocks, warps * 32, smem, s>>>(p);
   count_launch();
   THY_CUDA_CHECK(cudaGetLastError());
   return THY_OK;
@@ -308,17 +328,11 @@ thy_status launch_walk_pre(WalkParams p, long long grp_begin, long long grp_end,
 // of a round) draw in place.  Both launches read the actual walker count from device memory; a CTA with nothing to do
 // returns before it stages the model.
 template <int NT>
-thy_status launch_walk_nt(const WalkParams& p, int c_max, size_t smem, cudaStream_t s) {
-  const long long groups = (c_max + 7) / 8;
+thy_status launch_walk_nt(const WalkParams& p, const LikDev& lk, int c_max, int expected, cudaStream_t s) {
+  const long long groups = (c_max + 7) / 8, exp_groups = (std::min(expected, c_max) + 7) / 8;
   const long long pre = p.zpre ? std::min<long long>(p.pre_groups, groups) : 0;
-  THY_TRY((launch_walk_pre<NT, true>(p, 0, pre, smem, s)));
-  return launch_walk_pre<NT, false>(p, pre, groups, smem, s);
-}
-
-size_t walk_smem_bytes(const LikDev& lk, int nt) {
-  const int LDS = 8 * nt + 4;
-  const size_t rows = (size_t)round_up(lk.n_pad, 8 * WCH);
-  return rows * LDS * 8 + rows * 16 + (size_t)8 * nt * 32 + (size_t)WNW_MAX * 2 * nt * 32 * 8 + 16;
+  THY_TRY((launch_walk_pre<NT, true>(p, lk, 0, pre, exp_groups, s)));
+  return launch_walk_pre<NT, false>(p, lk, pre, groups, pre > 0 ? 1 : exp_groups, s);
 }
 
 }  // namespace
@@ -332,13 +346,13 @@ bool slq_walk_supported(const thy_model_s* m) {
   if (lk.dl != m->d || !own.contiguous || own.col_host.empty() || own.col_host[0] != 0) return false;
   const int nt = fused_nt_for(lk.dl);
   if (nt <= 0 || lk.lds != 8 * nt + 4) return false;
-  return walk_smem_bytes(lk, nt) <= (size_t)200 * 1024;
+  return walk_smem_bytes(lk, nt, WNW_MIN) <= WALK_SMEM_BUDGET;
 }
 
 thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long long Pl, int M, uint64_t seed,
                            const long long* round_dev, int rank, const int* sidx, const unsigned char* flags, double* x,
                            double* ll, double* lpr, const double* sigma, const double* scalars, int* accepted, cudaStream_t s,
-                           const float* zpre, const double* lacc, int pre_groups) {
+                           const float* zpre, const double* lacc, int pre_groups, int expected) {
   if (c_max <= 0) return THY_OK;
   const LikDev& lk = m->lik_dev[0]->view;
   WalkParams p{};
@@ -368,9 +382,8 @@ thy_status launch_slq_walk(thy_model_s* m, int c_max, const int* c_dev, long lon
   p.scalars = scalars;
   p.accepted = accepted;
   const int nt = fused_nt_for(lk.dl);
-  const size_t smem = walk_smem_bytes(lk, nt);
   switch (nt) {
-#define THY_WALK_CASE(N) case N: return launch_walk_nt<N>(p, c_max, smem, s);
+#define THY_WALK_CASE(N) case N: return launch_walk_nt<N>(p, lk, c_max, expected > 0 ? expected : c_max, s);
     THY_WALK_CASE(1) THY_WALK_CASE(2) THY_WALK_CASE(3) THY_WALK_CASE(4) THY_WALK_CASE(5) THY_WALK_CASE(7)
     THY_WALK_CASE(10) THY_WALK_CASE(13) THY_WALK_CASE(16)
 #undef THY_WALK_CASE
