@@ -281,6 +281,27 @@ def test_slq_duplicate_live_points_do_not_break_the_threshold_step():
     assert np.sum(np.diff(ll) == 0) > 0, "the scenario is meant to produce ties"
 
 
+@pytest.mark.parametrize("P,K,steps", [(4096, 1024, 1), (20000, 5000, 20), (3000, 37, 20)])
+def test_slq_bucket_sort_of_the_retired_values_equals_the_library_sort(P, K, steps, monkeypatch):
+    """A round's retired values are sorted by the bucket + rank kernels of slq_sort.cu (no library call in a round);
+    THY_SLQ_CUB_SORT=1 routes them through cub's radix sort instead.  Both are exact sorts of the same multiset, so the
+    whole retirement sequence -- heavy ties included (one walk step: most replacements are copies) -- is bit-identical."""
+    post, _, _ = _identity_model(6, seed=5)
+    cfg = t.SlqConfig(poolSize=P, abscissaNumber=2, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
+                      sampleParallelism=K, maxIterationCount=25 * K, minIterationCount=25 * K)
+    got = []
+    for cub in ("0", "1"):
+        monkeypatch.setenv("THY_SLQ_CUB_SORT", cub)
+        slq = t.SlqIntegratedPosterior.of(cfg, post, rngSeed=23, constrainedWalkSteps=steps)
+        slq.rebuildSampleSimulation()
+        got.append((slq.retiredLogLikelihoods().copy(), slq.abscissaResults()[0].copy()))
+        slq.close()
+    assert got[0][0].size == got[1][0].size and np.array_equal(got[0][0], got[1][0])
+    assert np.all(np.diff(got[0][0]) >= 0)
+    assert np.array_equal(got[0][1], got[1][1])
+    post.close()
+
+
 def test_slq_argument_checks_and_call_order():
     post, _, _ = _identity_model(2, seed=1)
     bad = t.SlqConfig(poolSize=2, abscissaNumber=1, domainScalingIncrement=0.1, targetAcceptanceProbability=0.3,

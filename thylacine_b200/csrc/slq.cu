@@ -46,6 +46,9 @@ struct thy_slq_s {
   thy::DevBuf<double> vals_raw, vals_sorted;             // retired values of the round, unordered / ascending
   thy::DevBuf<int> pair_in, pair_out;                    // slot ids beside the keys (drain / keepRetiredPoints)
   thy::DevBuf<unsigned char> cub_tmp, cub_tmp2;          // sort scratch: quadrature stream / main stream (pairs)
+  thy::DevBuf<unsigned long long> bs_minmax;              // bucket sort of a round's retired values (slq_sort.cu)
+  thy::DevBuf<unsigned int> bs_count, bs_cursor, bs_offset;
+  thy::DevBuf<double> bs_tmp;
   thy::DevBuf<double> Y, Yp, yl, ypr, tl, tpr;           // walkers of the per-step path
   thy::DevBuf<int> slot, accepted;
   thy::DevBuf<double> sigma, sig_part;                   // per-dimension spread of the live pool
@@ -81,6 +84,7 @@ struct thy_slq_s {
   uint64_t graph_launches = 0;
   bool use_graph = true;
   bool sort_sized = false;             // cub scratch sized (first round runs outside the graph)
+  bool cub_round_sort = false;         // THY_SLQ_CUB_SORT=1: a round's retired values through cub (measurement knob)
   // phase trace (thy_slq_set_trace / THY_SLQ_TRACE=1): CUDA-event times of the round's phases, plain launches
   bool trace = false;
   cudaEvent_t tev[8] = {};             // [0..5] phase boundaries on the main stream, [6], [7] around the pool spread
@@ -364,9 +368,13 @@ static EvidenceBuffers ev_buffers(thy_slq_s* h) {
   return e;
 }
 
-// Ascending sort of n values (the round's K retired log-likelihoods; the whole pool once, at the drain).  This is the
-// one library call left in a round: cub's radix sort on the quadrature stream, off the critical path.
+// Ascending sort of n values: a round's retired log-likelihoods go through the bucket sort of slq_sort.cu (no library
+// call in a round); the whole pool, once, at the drain, through cub's radix sort.
 static thy_status slq_sort_values(thy_slq_s* h, const double* in, double* out, int n, cudaStream_t s) {
+  if (n <= h->K && h->bs_tmp.ptr && !h->cub_round_sort) {
+    const BucketSortBuffers b{h->bs_minmax.ptr, h->bs_count.ptr, h->bs_cursor.ptr, h->bs_offset.ptr, h->bs_tmp.ptr};
+    return slq_bucket_sort(b, in, out, n, s);
+  }
   size_t bytes = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, n, 0, 64, s);
   if (bytes > h->cub_tmp.count) {
@@ -924,6 +932,8 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
   chk(h->pair_in.reserve((size_t)std::max<long long>(K, Pl))); chk(h->pair_out.reserve((size_t)std::max<long long>(K, Pl)));
   chk(h->Y.reserve((size_t)K * d)); chk(h->Yp.reserve((size_t)K * std::max(d, 1))); chk(h->yl.reserve(K)); chk(h->ypr.reserve(K));
   chk(h->tl.reserve(K)); chk(h->tpr.reserve(K)); chk(h->slot.reserve(K)); chk(h->accepted.reserve(K));
+  chk(h->bs_minmax.reserve(2)); chk(h->bs_count.reserve(SLQ_SORT_MAX_BUCKETS)); chk(h->bs_cursor.reserve(SLQ_SORT_MAX_BUCKETS));
+  chk(h->bs_offset.reserve(SLQ_SORT_MAX_BUCKETS + 1)); chk(h->bs_tmp.reserve(K));
   chk(h->sigma.reserve(d)); chk(h->sig_part.reserve((size_t)296 * 2 * d));
   chk(h->scalars.reserve(8));
   chk(h->ev_lt.reserve((size_t)h->A * KP)); chk(h->ev_segsum.reserve((size_t)h->A * nseg_max));
@@ -963,6 +973,12 @@ thy_status thy_slq_create(thy_model_t m, const thy_slq_config* cfg, uint64_t rng
       h->pre_groups = (int)((walkers + 7) / 8);
       chk(h->zpre.reserve((size_t)h->pre_groups * slq_walk_rng_floats_per_group(m, h->M)));
       chk(h->lacc.reserve((size_t)h->pre_groups * h->M * 8));
+    }
+    const char* cs = std::getenv("THY_SLQ_CUB_SORT");
+    h->cub_round_sort = cs && cs[0] == '1';
+    if (st == THY_OK) {
+      const BucketSortBuffers b{h->bs_minmax.ptr, h->bs_count.ptr, h->bs_cursor.ptr, h->bs_offset.ptr, h->bs_tmp.ptr};
+      chk(slq_bucket_sort_init(b, s));
     }
     const char* ng = std::getenv("THY_SLQ_GRAPH");
     h->use_graph = !(ng && ng[0] == '0');

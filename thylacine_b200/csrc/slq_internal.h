@@ -83,6 +83,19 @@ int slq_select_slices(long long Pl);
 thy_status slq_select_launch(const SelectBuffers& b, const double* keys, long long Pl, int world, int rank, int K,
                              double* vals, cudaStream_t s);
 
+// ---- exact sort of a round's retired values (slq_sort.cu) ----
+constexpr int SLQ_SORT_MAX_BUCKETS = 16384;
+struct BucketSortBuffers {
+  unsigned long long* minmax;   // [2] rest state (~0, 0)
+  unsigned int* count;          // [SLQ_SORT_MAX_BUCKETS] rest state 0
+  unsigned int* cursor;         // [SLQ_SORT_MAX_BUCKETS] rest state 0
+  unsigned int* offset;         // [SLQ_SORT_MAX_BUCKETS + 1]
+  double* tmp;                  // [n_max]
+};
+thy_status slq_bucket_sort_init(const BucketSortBuffers& b, cudaStream_t s);   // puts the counters in their rest state
+// out[0, n) = in[0, n) ascending (in and out distinct); six plain launches on s, no host interaction
+thy_status slq_bucket_sort(const BucketSortBuffers& b, const double* in, double* out, int n, cudaStream_t s);
+
 // ---- prior-mass simulation and quadrature (slq_evidence.cu) ----
 constexpr int EV_STATE = 12;   // doubles of carried state per abscissa
 // state: [0] logX assigned to the next point, [1] logX_{i-2}, [2] logX_{i-1}, [3] l_{i-1}, [4] pending points (0, 1, 2+),

@@ -313,7 +313,11 @@ thy_status launch_walk_pre(WalkParams p, const LikDev& lk, long long grp_begin, 
   const WalkShape shape = walk_cta_shape(std::min(expected_groups, grp_end - grp_begin), sms, WalkCta<NT, PRE>::MAXW);
   int warps = shape.warps;
   while (warps > 1 && walk_smem_bytes(lk, NT, warps) * shape.ctas_per_sm > WALK_SMEM_BUDGET) --warps;
-  const size_t smem = walk_smem_bytes(lk, NT, warps);
+  size_t smem = walk_smem_bytes(lk, NT, warps);
+  // One CTA per SM is only an even spread if the block scheduler cannot put two on one SM: kernels of the quadrature
+  // stream occupy some SMs for a few microseconds at the moment this grid is placed, and the CTAs they displace would
+  // double up elsewhere.  Asking for more than half of an SM's shared memory rules that out.
+  if (shape.ctas_per_sm == 1) smem = std::max(smem, (size_t)116 * 1024);
   THY_CUDA_CHECK(cudaFuncSetAttribute(k_slq_walk<NT, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // sized for the largest possible retire count; the kernel reads the actual one from device memory (grid-stride loop)
   long long blocks = (grp_end - grp_begin + warps - 1) / warps;
