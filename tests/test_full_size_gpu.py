@@ -51,7 +51,7 @@ def test_full_size_config5_nonlinear_cauchy_fd_16384_chains():
 def test_full_size_config4_slq_million_live_points_first_rounds():
     """Config 4's pool (50-d, 10^6 live points): the first rounds at full size.  Size-independent properties of the
     threshold step: every round retires exactly K points, the retired log-likelihoods are non-decreasing within and
-    across rounds, every live point sits above the last threshold, and the pool size is conserved.  (The run to
+    across rounds, no live point sits below the last threshold, and the pool size is conserved.  (The run to
     convergence against the analytic evidence is tools/run_multi.py --only c4full, profiles/r01_config4_slq_full_*.)"""
     d, P, K, rounds = 50, 1_000_000, 62_500, 6
     y = np.random.default_rng(20260104).standard_normal(d)
@@ -65,7 +65,9 @@ def test_full_size_config4_slq_million_live_points_first_rounds():
     assert ll.size == rounds * K
     assert np.all(np.diff(ll) >= 0)                                   # ascending within rounds and across thresholds
     x, live = slq.livePoints()
-    assert x.shape == (P, d) and np.all(live > ll[-1])
+    # no live point below the last threshold; AT it only exact copies of a retired point (a walker whose 40 proposals were
+    # all rejected is a copy of its survivor: ties are split by index order, test_slq_duplicate_live_points_...)
+    assert x.shape == (P, d) and np.all(live >= ll[-1]) and np.sum(live == ll[-1]) <= 4
     assert np.all(np.abs(x) <= 10.0)                                  # walkers never leave the prior's support
     want = -0.5 * np.sum((x[::1000] - y) ** 2, axis=1) - 0.5 * d * math.log(2 * math.pi)
     assert np.max(np.abs(live[::1000] - want) / np.abs(want)) < 1e-12  # stored log-likelihoods belong to the stored points
