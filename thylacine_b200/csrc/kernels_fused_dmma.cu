@@ -61,6 +61,7 @@ struct FusedParams {
   double pr_log_const;
   // resident variant: 8-row groups actually holding observations (rows beyond n are zero padding and are skipped)
   int nrg;
+  int stage_x;   // resident variant: chain rows reach shared memory by cp.async one group ahead (launcher decides)
   // HMC step folded into the output step (needs fuse_prior): see HmcFuse in kernels.h
   HmcFuse hmc;
 };
@@ -203,6 +204,49 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
       p.hmc.dH[chain] = dH;
     }
   }
+}
+
+// Output step of the RESIDENT kernel when nothing but value and gradient leave it (no fused HMC step) and chain rows are
+// 16-byte aligned pairs (d even, aligned base pointers).  emit_row_with_priors above costs ~1000 instructions per
+// 8-chain group -- prior records fetched from global memory coordinate by coordinate, a reconvergence region per prior
+// kind, scalar loads and stores -- and in the resident kernel a group is only 676 DMMAs: the warps spent 42 % of their
+// time outside their DMMA loops, so two warps per scheduler were both feeding the pipe a third of the time
+// (profiles/r02_resident_output_step.md).  Here the prior records come from shared memory (staged once per CTA as
+// (p0, p1, kind)), the X row is re-read as 13 double2 loads issued together, the prior terms are branch-free, and the
+// gradient leaves as 16-byte stores.  Same operations in the same order as the general step: bit-identical results.
+template <int NT>
+__device__ __forceinline__ void emit_row_fast(const FusedParams& p, const double4* __restrict__ pri, const double2* xrow,
+                                              long long chain, bool live, int q4, double qsum, const double (&ga)[NT][2]) {
+  const double lik = apply_logp(p.distribution, qsum, p.n, p.log_const);
+  const double sc = apply_scale(p.distribution, qsum, p.n, p.cauchy_sign);
+  double2* grow = reinterpret_cast<double2*>(p.grad + chain * p.d) + q4;   // xrow: the chain's row + q4 (global or staged)
+  double2 xv[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const bool ok = live && (8 * t + 2 * q4) < p.dl;
+    xv[t] = ok ? xrow[4 * t] : make_double2(0.0, 0.0);
+  }
+  double acc = 0.0;
+  int outside = 0;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int j = 8 * t + 2 * q4;
+    const bool ok = live && j < p.dl;
+    const double4 k0 = pri[j], k1 = pri[j + 1];   // beyond dl: kind = -1, no term
+    const double d0 = k0.x - xv[t].x, d1 = k1.x - xv[t].y;
+    const double w0 = d0 * k0.y, w1 = d1 * k1.y;
+    const bool g0 = k0.z == (double)PK_GAUSS_DIAG, g1 = k1.z == (double)PK_GAUSS_DIAG;
+    acc += g0 ? d0 * w0 : 0.0;
+    acc += g1 ? d1 * w1 : 0.0;
+    outside |= (int)(k0.z == (double)PK_UNIFORM) & ((int)!(xv[t].x >= k0.x) | (int)!(xv[t].x < k0.y));
+    outside |= (int)(k1.z == (double)PK_UNIFORM) & ((int)!(xv[t].y >= k1.x) | (int)!(xv[t].y < k1.y));
+    if (ok) grow[4 * t] = make_double2((g0 ? w0 : 0.0) + sc * ga[t][0], (g1 ? w1 : 0.0) + sc * ga[t][1]);
+  }
+  acc = quad_sum(acc);
+  const unsigned ballot = __ballot_sync(0xffffffffu, outside == 0);
+  const int lane = threadIdx.x & 31;
+  const bool inside_all = ((ballot >> (lane & ~3)) & 0xFu) == 0xFu;
+  if (live && q4 == 0) p.logp[chain] = (inside_all ? (-0.5 * acc + p.pr_log_const) : -INFINITY) + lik;
 }
 
 // Stream-K combine.  The last warp to deliver its segment of a (tile, warp) row group sums all segments, always in CTA
@@ -500,12 +544,22 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
   double* As = reinterpret_cast<double*>(smem);
   double2* Ys = reinterpret_cast<double2*>(smem + (size_t)rows * C::LDS * 8);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)rows * (C::LDS * 8 + 16));
+  double4* pri = reinterpret_cast<double4*>(smem + (size_t)rows * (C::LDS * 8 + 16) + 16);   // [8 NT + 1] (p0, p1, kind, -)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar, 1);
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
+  }
+  // fast output step (emit_row_fast): value + gradient only, rows of X / grad made of 16-byte aligned pairs
+  const bool fast_out = FUSE_PRIOR && WANT_GRAD && p.hmc.mode == HMC_FUSE_NONE && (p.d & 1) == 0 && (p.dl & 1) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(p.X) | reinterpret_cast<uintptr_t>(p.grad)) & 15) == 0;
+  if (FUSE_PRIOR) {
+    for (int j = threadIdx.x; j <= 8 * NT; j += blockDim.x) {
+      const bool in = j < p.dl;
+      pri[j] = make_double4(in ? p.pr_p0[j] : 0.0, in ? p.pr_p1[j] : 0.0, in ? (double)p.pr_kind[j] : -1.0, 0.0);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -526,13 +580,44 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
   const int off2_s1 = pi_s1 * C::LDS + g8;
   const long long ngroups = (p.B + 7) / 8;
   bool loaded = false;
-  for (long long grp = (long long)blockIdx.x * nwarps + warp; grp < ngroups; grp += (long long)gridDim.x * nwarps) {
+  // Chain rows one group ahead (stage_x): the 8 rows of a group are one contiguous block of X; the warp copies the block
+  // of its NEXT group into its own double buffer with 16-byte cp.async while it works on the current one, so neither the
+  // X fragments nor the output step's re-read of the row wait for global memory.
+  const bool stage = FUSE_PRIOR && p.stage_x != 0;
+  double* xw = reinterpret_cast<double*>(pri + 8 * NT + 1) + (size_t)warp * 2 * 8 * p.d;
+  const long long gstride = (long long)gridDim.x * nwarps;
+  auto issue_rows = [&](long long g, int b) {
+    if (g < ngroups) {
+      const long long c0 = g * 8;
+      const int nrows = (int)((p.B - c0 < 8) ? (p.B - c0) : 8);
+      const int chunks = nrows * p.d / 2;
+      const char* src = reinterpret_cast<const char*>(p.X + c0 * p.d);
+      const uint32_t dst = ptx::smem_u32(xw + (size_t)b * 8 * p.d);
+      for (int c = lane; c < chunks; c += 32) ptx::cp_async16(dst + 16u * c, src + 16 * (size_t)c);
+    }
+    ptx::cp_async_commit();   // an empty group keeps the wait count uniform
+  };
+  if (stage) issue_rows((long long)blockIdx.x * nwarps + warp, 0);
+  int buf = 0;
+  for (long long grp = (long long)blockIdx.x * nwarps + warp; grp < ngroups; grp += gstride, buf ^= 1) {
     const long long chain = grp * 8 + g8;
     double xf[C::KS];
+    const double* xsrow = xw + (size_t)buf * 8 * p.d + (size_t)g8 * p.d;
+    if (stage) {
+      issue_rows(grp + gstride, buf ^ 1);
+      ptx::cp_async_wait_group<1>();
+      __syncwarp();
 #pragma unroll
-    for (int kk = 0; kk < C::KS; ++kk) {
-      const int k = 4 * kk + q4;
-      xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + (FUSE_PRIOR ? k : p.col[k])] : 0.0;
+      for (int kk = 0; kk < C::KS; ++kk) {
+        const int k = 4 * kk + q4;
+        xf[kk] = (chain < p.B && k < p.dl) ? xsrow[k] : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < C::KS; ++kk) {
+        const int k = 4 * kk + q4;
+        xf[kk] = (chain < p.B && k < p.dl) ? p.X[chain * p.d + (FUSE_PRIOR ? k : p.col[k])] : 0.0;
+      }
     }
     if (!loaded) {
       ptx::mbar_wait(bar, 0);
@@ -560,7 +645,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
     }
     const double qsum = quad_sum(ssq);
     if (FUSE_PRIOR) {
-      emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qsum, ga);
+      if (WANT_GRAD && fast_out) {
+        const double2* xrow = reinterpret_cast<const double2*>(stage ? xsrow : p.X + chain * p.d) + q4;
+        emit_row_fast<WANT_GRAD ? NT : 1>(p, pri, xrow, chain, chain < p.B, q4, qsum, ga);
+      } else {
+        emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qsum, ga);
+      }
+      if (stage) __syncwarp();   // every lane is done with this buffer before the next iteration refills it
     } else if (chain < p.B) {
       if (q4 == 0) p.logp[chain] += apply_logp(p.distribution, qsum, p.n, p.log_const);
       if (WANT_GRAD) {
@@ -579,11 +670,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
   if (warp == 0 && !loaded) ptx::mbar_wait(bar, 0);
 }
 
-static size_t resident_smem_bytes(int nrg, int lds) { return (size_t)nrg * 8 * ((size_t)lds * 8 + 16) + 16; }
+static size_t resident_smem_bytes(int nrg, int lds) {   // A rows + (y, 1/var) + mbarrier + prior records (lds = 8 NT + 4)
+  return (size_t)nrg * 8 * ((size_t)lds * 8 + 16) + 16 + (size_t)(lds - 3) * 32;
+}
 
 template <int NT>
 thy_status launch_resident_nt(thy_model_s* m, FusedParams& p, bool want_grad, cudaStream_t s) {
-  const size_t smem = resident_smem_bytes(p.nrg, Cfg<NT>::LDS);
+  size_t smem = resident_smem_bytes(p.nrg, Cfg<NT>::LDS);
   const long long ngroups = (p.B + 7) / 8;
   const int sms = sm_count();
   // CTA width: enough warps to hold the work, few enough that small batches still reach every SM
@@ -593,6 +686,11 @@ thy_status launch_resident_nt(thy_model_s* m, FusedParams& p, bool want_grad, cu
   if (warps > 4) warps = NW;
   long long grid = (ngroups + warps - 1) / warps;
   if (grid > sms) grid = sms;
+  // chain rows staged one group ahead when there is room for two 8-row buffers per warp and rows are 16-byte pairs
+  const size_t xs_bytes = (size_t)warps * 2 * 8 * p.d * sizeof(double);
+  p.stage_x = (p.fuse_prior && (p.d & 1) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 &&
+               ngroups > 2 * grid * warps && smem + xs_bytes <= (size_t)224 * 1024) ? 1 : 0;   // pays from the third group on
+  if (p.stage_x) smem += xs_bytes;
   KernelTimer timer(m, s);
   auto launch = [&](auto kernel) -> thy_status {
     THY_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
