@@ -214,17 +214,25 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
 // (profiles/r02_resident_output_step.md).  Here the prior records come from shared memory (staged once per CTA as
 // (p0, p1, kind)), the X row is re-read as 13 double2 loads issued together, the prior terms are branch-free, and the
 // gradient leaves as 16-byte stores.  Same operations in the same order as the general step: bit-identical results.
-template <int NT>
+// MID: the leapfrog step folded in (HMC_FUSE_MID: second half kick of this step, first half kick and drift of the next,
+// HmcmcEngine.scala:55-80) -- momenta and next positions leave instead of the gradient, with the very operations of
+// emit_row_with_priors (__dmul_rn / __dadd_rn), so replay parity holds for both.
+template <int NT, bool MID>
 __device__ __forceinline__ void emit_row_fast(const FusedParams& p, const double4* __restrict__ pri, const double2* xrow,
                                               long long chain, bool live, int q4, double qsum, const double (&ga)[NT][2]) {
   const double lik = apply_logp(p.distribution, qsum, p.n, p.log_const);
   const double sc = apply_scale(p.distribution, qsum, p.n, p.cauchy_sign);
-  double2* grow = reinterpret_cast<double2*>(p.grad + chain * p.d) + q4;   // xrow: the chain's row + q4 (global or staged)
-  double2 xv[NT];
+  // xrow: the chain's row + q4 (global or staged)
+  double2* grow = MID ? nullptr : reinterpret_cast<double2*>(p.grad + chain * p.d) + q4;
+  double2* prow = MID ? reinterpret_cast<double2*>(p.hmc.p + chain * p.d) + q4 : nullptr;
+  double2* nrow = MID ? reinterpret_cast<double2*>(p.hmc.x_next + chain * p.d) + q4 : nullptr;
+  const double he = -p.hmc.eps / 2;
+  double2 xv[NT], pm[MID ? NT : 1];
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     const bool ok = live && (8 * t + 2 * q4) < p.dl;
     xv[t] = ok ? xrow[4 * t] : make_double2(0.0, 0.0);
+    if (MID) pm[t] = ok ? prow[4 * t] : make_double2(0.0, 0.0);
   }
   double acc = 0.0;
   int outside = 0;
@@ -240,7 +248,15 @@ __device__ __forceinline__ void emit_row_fast(const FusedParams& p, const double
     acc += g1 ? d1 * w1 : 0.0;
     outside |= (int)(k0.z == (double)PK_UNIFORM) & ((int)!(xv[t].x >= k0.x) | (int)!(xv[t].x < k0.y));
     outside |= (int)(k1.z == (double)PK_UNIFORM) & ((int)!(xv[t].y >= k1.x) | (int)!(xv[t].y < k1.y));
-    if (ok) grow[4 * t] = make_double2((g0 ? w0 : 0.0) + sc * ga[t][0], (g1 ? w1 : 0.0) + sc * ga[t][1]);
+    const double gj0 = (g0 ? w0 : 0.0) + sc * ga[t][0], gj1 = (g1 ? w1 : 0.0) + sc * ga[t][1];
+    if (!MID) {
+      if (ok) grow[4 * t] = make_double2(gj0, gj1);
+    } else if (ok) {
+      const double k0k = __dmul_rn(-gj0, he), k1k = __dmul_rn(-gj1, he);
+      const double pv0 = __dadd_rn(__dadd_rn(pm[MID ? t : 0].x, k0k), k0k), pv1 = __dadd_rn(__dadd_rn(pm[MID ? t : 0].y, k1k), k1k);
+      prow[4 * t] = make_double2(pv0, pv1);
+      nrow[4 * t] = make_double2(__dadd_rn(xv[t].x, __dmul_rn(pv0, p.hmc.eps)), __dadd_rn(xv[t].y, __dmul_rn(pv1, p.hmc.eps)));
+    }
   }
   acc = quad_sum(acc);
   const unsigned ballot = __ballot_sync(0xffffffffu, outside == 0);
@@ -553,8 +569,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
     ptx::fence_proxy_async();
   }
   // fast output step (emit_row_fast): value + gradient only, rows of X / grad made of 16-byte aligned pairs
-  const bool fast_out = FUSE_PRIOR && WANT_GRAD && p.hmc.mode == HMC_FUSE_NONE && (p.d & 1) == 0 && (p.dl & 1) == 0 &&
-                        ((reinterpret_cast<uintptr_t>(p.X) | reinterpret_cast<uintptr_t>(p.grad)) & 15) == 0;
+  const bool fast_mid = p.hmc.mode == HMC_FUSE_MID;
+  const bool fast_out = FUSE_PRIOR && WANT_GRAD && (p.d & 1) == 0 && (p.dl & 1) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 &&
+                        (fast_mid ? ((reinterpret_cast<uintptr_t>(p.hmc.p) | reinterpret_cast<uintptr_t>(p.hmc.x_next)) & 15) == 0
+                                  : (p.hmc.mode == HMC_FUSE_NONE && (reinterpret_cast<uintptr_t>(p.grad) & 15) == 0));
   if (FUSE_PRIOR) {
     for (int j = threadIdx.x; j <= 8 * NT; j += blockDim.x) {
       const bool in = j < p.dl;
@@ -647,7 +666,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
     if (FUSE_PRIOR) {
       if (WANT_GRAD && fast_out) {
         const double2* xrow = reinterpret_cast<const double2*>(stage ? xsrow : p.X + chain * p.d) + q4;
-        emit_row_fast<WANT_GRAD ? NT : 1>(p, pri, xrow, chain, chain < p.B, q4, qsum, ga);
+        if (fast_mid) emit_row_fast<WANT_GRAD ? NT : 1, true>(p, pri, xrow, chain, chain < p.B, q4, qsum, ga);
+        else emit_row_fast<WANT_GRAD ? NT : 1, false>(p, pri, xrow, chain, chain < p.B, q4, qsum, ga);
       } else {
         emit_row_with_priors<NT, WANT_GRAD>(p, chain, chain < p.B, q4, qsum, ga);
       }
