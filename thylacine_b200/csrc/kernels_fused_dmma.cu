@@ -62,6 +62,7 @@ struct FusedParams {
   // resident variant: 8-row groups actually holding observations (rows beyond n are zero padding and are skipped)
   int nrg;
   int stage_x;   // resident variant: chain rows reach shared memory by cp.async one group ahead (launcher decides)
+  int split;     // resident variant: 1, or 2 = two warps share a group's row blocks (small batches; launcher decides)
   // HMC step folded into the output step (needs fuse_prior): see HmcFuse in kernels.h
   HmcFuse hmc;
 };
@@ -133,13 +134,13 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
         if (kd[tt][h] == PK_GAUSS_DIAG) {
           const double dl = q0[tt][h] - xv[tt][h];
           const double w = dl * q1[tt][h];
-          acc += dl * w;
+          acc = fma(dl, w, acc);   // explicit: emit_row_fast must round the same way
           gj = w;
         } else if (kd[tt][h] == PK_UNIFORM) {
           inside = inside && (xv[tt][h] >= q0[tt][h]) && (xv[tt][h] < q1[tt][h]);
         }
         if (WANT_GRAD) {
-          gj = gj + sc * ga[WANT_GRAD ? (t0 + tt) : 0][h];
+          gj = fma(sc, ga[WANT_GRAD ? (t0 + tt) : 0][h], gj);
           if (mode == HMC_FUSE_NONE) {
             grow[j] = gj;
           } else if (mode == HMC_FUSE_MID) {
@@ -189,7 +190,7 @@ __device__ __forceinline__ void emit_row_with_priors(const FusedParams& p, long 
             const double xj = xrow[j];
             const double gpr = (p.pr_kind[j] == PK_GAUSS_DIAG) ? (p.pr_p0[j] - xj) * p.pr_p1[j] : 0.0;
             p.hmc.x[chain * p.d + j] = xj;
-            p.hmc.g[chain * p.d + j] = gpr + sc * ga[WANT_GRAD ? t : 0][h];
+            p.hmc.g[chain * p.d + j] = fma(sc, ga[WANT_GRAD ? t : 0][h], gpr);
           }
         }
       }
@@ -244,11 +245,11 @@ __device__ __forceinline__ void emit_row_fast(const FusedParams& p, const double
     const double d0 = k0.x - xv[t].x, d1 = k1.x - xv[t].y;
     const double w0 = d0 * k0.y, w1 = d1 * k1.y;
     const bool g0 = k0.z == (double)PK_GAUSS_DIAG, g1 = k1.z == (double)PK_GAUSS_DIAG;
-    acc += g0 ? d0 * w0 : 0.0;
-    acc += g1 ? d1 * w1 : 0.0;
+    acc = g0 ? fma(d0, w0, acc) : acc;   // the general step's fma, coordinate by coordinate
+    acc = g1 ? fma(d1, w1, acc) : acc;
     outside |= (int)(k0.z == (double)PK_UNIFORM) & ((int)!(xv[t].x >= k0.x) | (int)!(xv[t].x < k0.y));
     outside |= (int)(k1.z == (double)PK_UNIFORM) & ((int)!(xv[t].y >= k1.x) | (int)!(xv[t].y < k1.y));
-    const double gj0 = (g0 ? w0 : 0.0) + sc * ga[t][0], gj1 = (g1 ? w1 : 0.0) + sc * ga[t][1];
+    const double gj0 = fma(sc, ga[t][0], g0 ? w0 : 0.0), gj1 = fma(sc, ga[t][1], g1 ? w1 : 0.0);
     if (!MID) {
       if (ok) grow[4 * t] = make_double2(gj0, gj1);
     } else if (ok) {
@@ -604,7 +605,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
   // X fragments nor the output step's re-read of the row wait for global memory.
   const bool stage = FUSE_PRIOR && p.stage_x != 0;
   double* xw = reinterpret_cast<double*>(pri + 8 * NT + 1) + (size_t)warp * 2 * 8 * p.d;
-  const long long gstride = (long long)gridDim.x * nwarps;
   auto issue_rows = [&](long long g, int b) {
     if (g < ngroups) {
       const long long c0 = g * 8;
@@ -616,14 +616,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
     }
     ptx::cp_async_commit();   // an empty group keeps the wait count uniform
   };
-  if (stage) issue_rows((long long)blockIdx.x * nwarps + warp, 0);
+  // Small batches (split == 2): a group is the work of a PAIR of warps.  With one group per warp and at most four warps on
+  // an SM every warp is alone on its scheduler and its 676 DMMAs issue 26 clocks apart (one dependent chain: 62 % of the
+  // pipe); two warps that take alternate row blocks of the same group -- both GEMMs of a row block stay in one warp --
+  // finish in 338 x 32 clocks, and the odd warp hands its partial gradient and sum of squares to the even one through
+  // shared memory (one named barrier per group, buffers alternate with the iteration).
+  const int split = p.split == 2 ? 2 : 1;
+  const int slot = split == 2 ? (warp >> 1) : warp, sw = split == 2 ? (warp & 1) : 0, slots = nwarps / split;
+  double2* exch = reinterpret_cast<double2*>(pri + 8 * NT + 1) + (size_t)slot * 2 * (NT + 1) * 32 + lane;
+  const long long gfirst = (long long)blockIdx.x * slots + slot, gstep = (long long)gridDim.x * slots;
+  if (stage) issue_rows(gfirst, 0);
   int buf = 0;
-  for (long long grp = (long long)blockIdx.x * nwarps + warp; grp < ngroups; grp += gstride, buf ^= 1) {
+  for (long long grp = gfirst; grp < ngroups; grp += gstep, buf ^= 1) {
     const long long chain = grp * 8 + g8;
     double xf[C::KS];
     const double* xsrow = xw + (size_t)buf * 8 * p.d + (size_t)g8 * p.d;
     if (stage) {
-      issue_rows(grp + gstride, buf ^ 1);
+      issue_rows(grp + gstep, buf ^ 1);
       ptx::cp_async_wait_group<1>();
       __syncwarp();
 #pragma unroll
@@ -654,6 +663,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
     int rg = 0;
     for (int blk = 0; blk < nblocks; ++blk) {
       const int cnt = base + (blk < extra ? 1 : 0);
+      if (split == 2 && (blk & 1) != sw) {   // the other warp of the pair takes this block
+        rg += cnt;
+        continue;
+      }
       const double* Ab = As + (size_t)rg * 8 * C::LDS;
       const double2* Yb = Ys + rg * 8;
       if (cnt == 4) resident_rows<NT, 4, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
@@ -661,6 +674,27 @@ __global__ void __launch_bounds__(NW * 32, 1) k_resident_dmma(const FusedParams 
       else if (cnt == 2) resident_rows<NT, 2, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
       else resident_rows<NT, 1, WANT_GRAD>(Ab, Yb, off1, off2_s0, off2_s1, pi_s0, pi_s1, xf, ga, ssq);
       rg += cnt;
+    }
+    if (split == 2) {
+      double2* ex = exch + (size_t)buf * (NT + 1) * 32;
+      if (sw == 1) {
+        if (WANT_GRAD) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) ex[t * 32] = make_double2(ga[WANT_GRAD ? t : 0][0], ga[WANT_GRAD ? t : 0][1]);
+        }
+        ex[NT * 32] = make_double2(ssq, 0.0);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+      if (sw == 1) continue;   // the even warp finishes the group
+      if (WANT_GRAD) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const double2 v = ex[t * 32];
+          ga[WANT_GRAD ? t : 0][0] += v.x;
+          ga[WANT_GRAD ? t : 0][1] += v.y;
+        }
+      }
+      ssq += ex[NT * 32].x;
     }
     const double qsum = quad_sum(ssq);
     if (FUSE_PRIOR) {
@@ -699,16 +733,23 @@ thy_status launch_resident_nt(thy_model_s* m, FusedParams& p, bool want_grad, cu
   size_t smem = resident_smem_bytes(p.nrg, Cfg<NT>::LDS);
   const long long ngroups = (p.B + 7) / 8;
   const int sms = sm_count();
-  // CTA width: enough warps to hold the work, few enough that small batches still reach every SM
+  // CTA width: enough warps to hold the work, few enough that small batches still reach every SM.  When that leaves at
+  // most four warps on an SM (one per scheduler), a group becomes the work of a pair of warps (p.split = 2).
   int warps = (int)((ngroups + sms - 1) / sms);
   warps = warps < 1 ? 1 : (warps > NW ? NW : warps);
   if (warps == 3) warps = 4;
   if (warps > 4) warps = NW;
+  const size_t exch_bytes = (size_t)(NW / 2) * 2 * (Cfg<NT>::KS / 2 + 1) * 32 * 16;
+  p.split = (2 * warps <= NW && p.nrg > JG && smem + exch_bytes <= (size_t)224 * 1024) ? 2 : 1;
   long long grid = (ngroups + warps - 1) / warps;
   if (grid > sms) grid = sms;
+  if (p.split == 2) {
+    warps *= 2;   // the same groups per CTA, two warps each
+    smem += exch_bytes;
+  }
   // chain rows staged one group ahead when there is room for two 8-row buffers per warp and rows are 16-byte pairs
   const size_t xs_bytes = (size_t)warps * 2 * 8 * p.d * sizeof(double);
-  p.stage_x = (p.fuse_prior && (p.d & 1) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 &&
+  p.stage_x = (p.split == 1 && p.fuse_prior && (p.d & 1) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 &&
                ngroups > 2 * grid * warps && smem + xs_bytes <= (size_t)224 * 1024) ? 1 : 0;   // pays from the third group on
   if (p.stage_x) smem += xs_bytes;
   KernelTimer timer(m, s);
