@@ -12,7 +12,8 @@
 //                the early passes, so equal digits are aggregated with match.any first), merges into a global
 //                histogram, and after the barrier every CTA scans it and extends the prefix by one digit.  After the
 //                last pass the prefix IS the K-th smallest key, bit for bit, and the remainder says how many of the keys
-//                equal to it still have to go.
+//                equal to it still have to go.  EARLY EXIT: as soon as the decided bin holds <= 64 keys they are
+//                collected and ranked directly (typically after the third pass: three passes and two barriers saved).
 //   count        per 2048-key slice of the GLOBAL key array: keys below / equal to the threshold; the retired VALUES
 //                (all keys below the threshold + the ties that go) are appended, unordered, to the quadrature's input
 //                (they are sorted on the quadrature stream, off the critical path).
@@ -34,6 +35,7 @@ constexpr int ST = 512;            // threads per CTA
 constexpr int SW = ST / 32;        // warps
 constexpr int SEL_BINS = 2048;
 constexpr int NPASS = 6;
+constexpr int CAND_MAX = 64;       // early exit: this few keys left in the decided bin are ranked directly
 __constant__ int c_shift[NPASS] = {53, 42, 31, 20, 9, 0};
 __constant__ int c_bits[NPASS] = {11, 11, 11, 11, 11, 9};
 
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(ST, 1) k_slq_select(const SelectArgs a) {
   __shared__ unsigned int s_remaining, s_bin;
   __shared__ long long s_tie_base;
   __shared__ int s_ret_base;
+  __shared__ unsigned long long s_cand[CAND_MAX];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const unsigned int G = gridDim.x;
   const long long n = a.Pl * a.world;
@@ -183,6 +186,57 @@ __global__ void __launch_bounds__(ST, 1) k_slq_select(const SelectArgs a) {
     remaining = s_remaining;
     bin_count = s_bin;
     __syncthreads();
+    // ---- early exit ----
+    // Log-likelihoods of a pool share their sign and (almost) their exponent, so after the third pass the decided bin
+    // typically holds one or two keys and the remaining passes would histogram a handful of keys with a grid barrier
+    // each.  Once at most CAND_MAX keys are left they are collected (one more look at the keys in registers, one grid
+    // barrier) and every CTA ranks them directly: same threshold, same tie counts, bit for bit.  The candidate list
+    // lives in the last pass's histogram, which an early exit leaves unused and the re-arm step zeroes.
+    if (pass < NPASS - 1 && bin_count <= (unsigned int)CAND_MAX) {
+      unsigned int* cc = a.b.hist + (NPASS - 1) * SEL_BINS;
+      unsigned long long* cand = reinterpret_cast<unsigned long long*>(cc + 2);
+      auto collect = [&](bool valid, unsigned long long k) {
+        if (valid && (k >> shift) == (prefix >> shift)) {
+          const unsigned int idx = atomicAdd(cc, 1u);
+          if (idx < (unsigned int)CAND_MAX) cand[idx] = k;
+        }
+      };
+      if (in_regs) {
+#pragma unroll
+        for (int q = 0; q < RK; ++q) {
+          const long long i = ((long long)q * G + blockIdx.x) * ST + threadIdx.x;
+          collect(i < n, kr[q]);
+        }
+      } else {
+        const long long stride = (long long)G * ST;
+        for (long long i = (long long)blockIdx.x * ST + threadIdx.x; i < n; i += stride) collect(true, key_image(a.keys[i]));
+      }
+      grid_barrier(bar, G);
+      const unsigned int nc = bin_count;
+      if (threadIdx.x < nc) s_cand[threadIdx.x] = __ldcg(&cand[threadIdx.x]);
+      __syncthreads();
+      if (threadIdx.x < nc) {
+        const unsigned long long me = s_cand[threadIdx.x];
+        unsigned int less = 0, eq = 0, eq_before = 0;
+        for (unsigned int j = 0; j < nc; ++j) {
+          const unsigned long long o = s_cand[j];
+          less += (o < me) ? 1u : 0u;
+          eq += (o == me) ? 1u : 0u;
+          eq_before += (o == me && j < threadIdx.x) ? 1u : 0u;
+        }
+        if (less < remaining && remaining <= less + eq && eq_before == 0) {   // exactly one thread
+          s_prefix = me;
+          s_remaining = remaining - less;
+          s_bin = eq;
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      remaining = s_remaining;
+      bin_count = s_bin;
+      __syncthreads();
+      break;
+    }
   }
   // prefix = image of the K-th smallest key; `remaining` of the `bin_count` keys equal to it retire
   const unsigned long long thr = prefix;
