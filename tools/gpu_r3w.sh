@@ -1,6 +1,6 @@
 #!/bin/bash
 # final validation of the round on one GPU: all GPU tests, smoke, the bench line (+ clock record)
-O=gpurun_out/r4i; mkdir -p $O
+O=gpurun_out/r4m; mkdir -p $O
 timeout 1500 python -m pytest tests/ -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest_gpu rc=$?" >> $O/rc.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/rc.txt
 ( while true; do nvidia-smi --query-gpu=timestamp,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active,power.draw --format=csv,noheader >> $O/clocks.csv; sleep 0.5; done ) & CL=$!
@@ -10,7 +10,7 @@ THY_SLQ_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control
 cat $O/rc.txt; tail -n 4 $O/pytest_gpu.log; tail -n 2 $O/smoke.log; tail -n 3 $O/bench_n1.err
 python - <<'PY'
 import json
-j=json.loads(open('gpurun_out/r4i/bench_n1.json').read().strip().splitlines()[-1])
+j=json.loads(open('gpurun_out/r4m/bench_n1.json').read().strip().splitlines()[-1])
 print(j["value"], j["e2e"]["value"], j["roofline"]["frac"], j["hmc"]["value"], j["reduced_flop"]["chains_per_gpu_65536"]["value"], j["gpu_launches"], j["clocks"])
 sl=j["slq"]; print(sl["seconds"], sl["error"], sl["within_tolerance"], sl["phase_us_per_round"])
 PY
