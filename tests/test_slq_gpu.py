@@ -190,7 +190,7 @@ def test_slq_linear_model_gaussian_prior_and_posterior_samples():
     assert abs(got - want) < tol + 0.05
 
 
-@pytest.mark.parametrize("case", ["identity_uniform", "linear_gaussian", "linear_cauchy"])
+@pytest.mark.parametrize("case", ["identity_uniform", "linear_gaussian", "linear_cauchy", "linear_gaussian_wide"])
 def test_slq_fused_walk_kernel_matches_the_per_step_kernels(case):
     """The one-kernel replacement step (slq_walk.cu: spawn + M steps + commit, walker state in DMMA fragments) against
     the per-step kernels: same random numbers, same proposals; the log-likelihoods differ only in summation order, so
@@ -200,11 +200,11 @@ def test_slq_fused_walk_kernel_matches_the_per_step_kernels(case):
         d = 7
         post, y, _ = _identity_model(d, seed=3, uniform=True)
     else:
-        d, n = 21, 45
+        d, n = (100, 120) if case == "linear_gaussian_wide" else (21, 45)   # wide: the 8-warp, 255-register instantiation
         A = rng.standard_normal((n, d)) / math.sqrt(d)
         y = A @ rng.standard_normal(d) + 0.3 * rng.standard_normal(n)
-        lik = (t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.6), "theta") if case == "linear_gaussian"
-               else t.CauchyLikelihood.of(A, y, np.full(n, 0.6), "theta"))
+        lik = (t.CauchyLikelihood.of(A, y, np.full(n, 0.6), "theta") if case == "linear_cauchy"
+               else t.GaussianLinearLikelihood.of(A, y, np.full(n, 0.6), "theta"))
         post = t.UnnormalisedPosterior([t.GaussianPrior.fromConfidenceIntervals("theta", np.zeros(d), np.full(d, 4.0))], [lik])
     P, K = 4096, 1000                                                        # 1000 walkers: a ragged last group of 8
     cfg = t.SlqConfig(poolSize=P, abscissaNumber=2, domainScalingIncrement=0.05, targetAcceptanceProbability=0.3,
