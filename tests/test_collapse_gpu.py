@@ -52,6 +52,40 @@ def test_collapsed_posterior_is_the_same_function(d, n, B):
     post.close()
 
 
+@pytest.mark.parametrize("d,B", [(100, 24_003), (34, 40_000)])
+def test_resident_kernel_large_batch_with_staged_rows_matches_small_batches_and_the_oracle(d, B):
+    """The resident kernel changes shape with the batch: up to ~4 700 chains a group of 8 chains is the work of a PAIR of
+    warps, from ~19 000 chains on the chain rows of the next group are staged in shared memory by cp.async while the
+    current one computes (kernels_fused_dmma.cu, k_resident_dmma).  One large device-resident batch (staged rows, ragged
+    last group) against the same points in chunks of 2 000 (warp pairs, no staging): same function to summation order;
+    and against the oracle's canonical evaluation at 1e-10."""
+    import torch
+    n = 1500
+    prob = linear_gaussian_problem(d, n, seed=300 + d)
+    col = _posterior(prob).collapsed()
+    X = typical_set_points(prob, B, seed=2)
+    Xd = torch.from_numpy(X).cuda()
+    lp = torch.empty(B, dtype=torch.float64, device="cuda")
+    g = torch.empty(B, d, dtype=torch.float64, device="cuda")
+    col.logPdfGradBatchDevice(B, Xd.data_ptr(), lp.data_ptr(), g.data_ptr())
+    col.synchronize()
+    assert col.lastKernelPath == "resident_dmma"
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    lp_small = np.empty(B)
+    g_small = np.empty((B, d))
+    for b0 in range(0, B, 2000):
+        lp_small[b0:b0 + 2000], g_small[b0:b0 + 2000] = col.logPdfGradBatch(X[b0:b0 + 2000])
+    assert rel_err_logp(lp, lp_small) < 1e-13 and rel_err_grad(g, g_small) < 1e-12
+    pick = np.r_[0:64, B - 64:B]
+    want_lp, want_g = o.linear_gaussian_batch(prob["A"], prob["y"], prob["var"], X[pick], prior_mean=prob["pm"],
+                                              prior_var=prob["pvar"])
+    assert rel_err_logp(lp[pick], want_lp) < TOL and rel_err_grad(g[pick], want_g) < TOL
+    lv = torch.empty(B, dtype=torch.float64, device="cuda")                        # value only: the general output step
+    col.logPdfGradBatchDevice(B, Xd.data_ptr(), lv.data_ptr(), None)
+    col.synchronize()
+    assert np.array_equal(lv.cpu().numpy(), lp)
+
+
 def test_collapse_multi_label_offset_two_likelihoods_and_uniform_prior():
     rng = np.random.default_rng(21)
     n1, n2 = 70, 45
